@@ -1,0 +1,93 @@
+// Per-list device building blocks: draws, ordering networks, ListMLE forward/backward.
+#pragma once
+#include "pld_common.cuh"
+
+namespace pld {
+
+enum { SRC_PHILOX = 0, SRC_FED_SEL = 1, SRC_FED_RANK = 2 };
+
+struct ListParams {
+  const float* gt;             // [B, HW]
+  const int32_t* valid_flat;   // [B, valid_stride]
+  const int32_t* n_valid;      // [B]
+  const float* pred;           // [B, HW]
+  const int32_t* sel_in;       // [B, n, K]   (SRC_FED_SEL)
+  const float* rank_in;        // [B, n, K, 2] (SRC_FED_RANK)
+  float* rank_out;             // [B, n, K, 2] nullable
+  int32_t* sel_out;            // [B, n, K] nullable
+  float* per_list;             // [B*n] nullable
+  float* grad;                 // [B, HW] nullable
+  float* loss;                 // [1]
+  double* loss_sum;            // [1] nullable
+  double* partials;
+  unsigned int* ticket;
+  int* status;
+  int B, HW, valid_stride, n, K;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi16;
+  int image_base;
+  float scale;
+};
+
+#define PLD_LOG_EPS (-23.025850929940457f) /* float32(log(1e-10)), TF-Ranking _EPSILON */
+
+// compare-exchange, descending (a >= b afterwards)
+__device__ __forceinline__ void ce_desc(uint64_t& a, uint64_t& b) {
+  const bool sw = a < b;
+  const uint64_t hi = sw ? b : a, lo = sw ? a : b;
+  a = hi; b = lo;
+}
+__device__ __forceinline__ void ce_desc(uint64_t& a, uint64_t& b, uint32_t& pa, uint32_t& pb) {
+  const bool sw = a < b;
+  const uint64_t hi = sw ? b : a, lo = sw ? a : b;
+  const uint32_t ph = sw ? pb : pa, pl = sw ? pa : pb;
+  a = hi; b = lo; pa = ph; pb = pl;
+}
+
+// Register sorting network for K keys, descending.  K == 5 uses the optimal 9-comparator
+// network; other K use the insertion network (K(K-1)/2 comparators, fully unrolled).
+template <int K, bool PAYLOAD>
+__device__ __forceinline__ void sort_desc_regs(uint64_t (&key)[K], uint32_t (&pay)[K]) {
+#define PLD_CE(i, j)                                        \
+  do {                                                      \
+    if (PAYLOAD) ce_desc(key[i], key[j], pay[i], pay[j]);   \
+    else ce_desc(key[i], key[j]);                           \
+  } while (0)
+  if constexpr (K == 5) {
+    PLD_CE(0, 1); PLD_CE(3, 4); PLD_CE(2, 4); PLD_CE(2, 3); PLD_CE(1, 4);
+    PLD_CE(0, 3); PLD_CE(0, 2); PLD_CE(1, 3); PLD_CE(1, 2);
+  } else {
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+#pragma unroll
+      for (int j = i; j > 0; --j) PLD_CE(j - 1, j);
+    }
+  }
+#undef PLD_CE
+}
+
+// ListMLE on K scores already in sorted (label-descending) order, all in registers.
+// nll = sum_k log(S_k) - (s_k - m),  S_k = sum_{j>=k} exp(s_j - m)   (reverse cumsum)
+// g_k = exp(s_k - m) * sum_{i<=k} 1/S_i - 1
+template <int K>
+__device__ __forceinline__ float listmle_regs(const float (&s)[K], float (&g)[K]) {
+  float m = s[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+  float e[K], S[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) e[k] = expf(s[k] - m);
+  float run = 0.f;
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) { run += e[k]; S[k] = run; }
+  float nll = 0.f, c = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    // the last term is log(e_k) - (s_k - m) == 0 analytically; keep TF's arithmetic anyway
+    nll += logf(S[k]) - (s[k] - m);
+    c += 1.0f / S[k];
+    g[k] = e[k] * c - 1.0f;
+  }
+  return nll;
+}
+
+}  // namespace pld

@@ -1,0 +1,343 @@
+// Group-per-list kernels for ranking_size 17..512: LPL lanes x IPL register slots per list.
+// Ordering = bitonic network over LPL*IPL slots (shuffles across lanes, register swaps inside
+// a lane); ListMLE = lane-local scans + shuffle scans for the reverse cumsum / prefix sums.
+#include "pld_lists.cuh"
+
+namespace pld {
+
+template <int LPL, int IPL, bool PAYLOAD>
+__device__ __forceinline__ void bitonic_desc(uint64_t (&key)[IPL], uint32_t (&pay)[IPL], int gl) {
+  constexpr int N = LPL * IPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= IPL) {
+        const int lm = j / IPL;
+        const bool lower = (gl & lm) == 0;
+        const bool up = (gl & (k / IPL)) == 0;  // k/IPL == LPL on the last merge -> always up
+        const bool keep_max = (up == lower);
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[i], lm);
+          const bool take = keep_max ? (other > key[i]) : (other < key[i]);
+          if (PAYLOAD) {
+            const uint32_t op = __shfl_xor_sync(0xffffffffu, pay[i], lm);
+            pay[i] = take ? op : pay[i];
+          }
+          key[i] = take ? other : key[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          if ((i & j) == 0) {
+            const bool up = (((gl * IPL + i) & k) == 0);
+            uint64_t a = key[i], b = key[i | j];
+            const bool sw = up ? (a < b) : (a > b);
+            key[i] = sw ? b : a;
+            key[i | j] = sw ? a : b;
+            if (PAYLOAD) {
+              const uint32_t pa = pay[i], pb = pay[i | j];
+              pay[i] = sw ? pb : pa;
+              pay[i | j] = sw ? pa : pb;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int LPL>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPL>
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPL>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPL>
+__device__ __forceinline__ bool group_all(bool v, int lane) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, v);
+  const uint32_t gmask = (LPL == 32) ? 0xffffffffu : (((1u << LPL) - 1u) << (lane & ~(LPL - 1)));
+  return (bal & gmask) == gmask;
+}
+// sum of `v` over lanes of the group with a larger / smaller group-lane index
+template <int LPL>
+__device__ __forceinline__ float group_excl_suffix(float v, int gl) {
+  float x = __shfl_down_sync(0xffffffffu, v, 1, LPL);
+  if (gl + 1 >= LPL) x = 0.f;
+#pragma unroll
+  for (int d = 1; d < LPL; d <<= 1) {
+    const float t = __shfl_down_sync(0xffffffffu, x, d, LPL);
+    if (gl + d < LPL) x += t;
+  }
+  return x;
+}
+template <int LPL>
+__device__ __forceinline__ float group_excl_prefix(float v, int gl) {
+  float x = __shfl_up_sync(0xffffffffu, v, 1, LPL);
+  if (gl == 0) x = 0.f;
+#pragma unroll
+  for (int d = 1; d < LPL; d <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, x, d, LPL);
+    if (gl >= d) x += t;
+  }
+  return x;
+}
+
+template <int LPL, int IPL, int SRC, bool LOSS>
+__global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
+  constexpr int GPW = 32 / LPL;    // groups per warp
+  constexpr int GPB = 256 / LPL;   // groups per block
+  const int K = P.K;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPL - 1);
+  const size_t map_off = (size_t)b * (size_t)P.HW;
+  const float* __restrict__ gt = P.gt + map_off;
+  const float* __restrict__ pred = P.pred + map_off;
+  float local = 0.f;
+  int bad = 0;
+
+  uint32_t M = 1, thresh = 0;
+  const int32_t* __restrict__ vflat = nullptr;
+  if (SRC != SRC_FED_RANK) {
+    const int m = P.n_valid[b];
+    if (m <= 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
+    else { M = (uint32_t)m; thresh = (0u - M) % M; }
+    vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
+  }
+
+  if (M != 0) {
+    for (int l0 = blockIdx.x * GPB + (threadIdx.x >> 5) * GPW; l0 < P.n; l0 += gridDim.x * GPB) {
+      const int lraw = l0 + lane / LPL;
+      const bool active = lraw < P.n;
+      const int l = active ? lraw : (P.n - 1);
+      const size_t list_id = (size_t)b * (size_t)P.n + (size_t)l;
+      int p[IPL];
+      float lab[IPL];
+      uint32_t inval = 0;
+
+      if (SRC == SRC_FED_RANK) {
+        const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) + list_id * K;
+        bool ok = true;  // locally sorted and valid
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          const int e = gl * IPL + i;
+          p[i] = 0;
+          lab[i] = 0.f;
+          if (e < K) {
+            const float2 v = __ldg(rin + e);
+            int q = (int)v.x;
+            if (q < 0 || q >= P.HW) { bad |= PLD_ST_BAD_INDEX; q = 0; }
+            p[i] = q;
+            lab[i] = v.y;
+            ok = ok && (v.y >= 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 1; i < IPL; ++i)
+          if (gl * IPL + i < K) ok = ok && (lab[i - 1] >= lab[i]);
+        {
+          const float nxt = __shfl_down_sync(0xffffffffu, lab[0], 1, LPL);
+          if (gl + 1 < LPL && (gl + 1) * IPL < K) ok = ok && (lab[IPL - 1] >= nxt);
+        }
+        const bool need_sort = __any_sync(0xffffffffu, !ok);
+        if (need_sort) {
+          float mn = 3.402823466e38f;
+#pragma unroll
+          for (int i = 0; i < IPL; ++i)
+            if (gl * IPL + i < K) mn = fminf(mn, lab[i] >= 0.f ? lab[i] : 0.f);
+          mn = group_min<LPL>(mn);
+          const float inv_key = mn - 1e-6f;
+          uint64_t key[IPL];
+          uint32_t pay[IPL];
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) {
+            const int e = gl * IPL + i;
+            if (e < K) {
+              const bool v = lab[i] >= 0.f;
+              key[i] = ((uint64_t)float_to_ordered(v ? lab[i] : inv_key) << 32) | (uint32_t)(0xFFFF - e);
+              pay[i] = (uint32_t)p[i] | (v ? 0u : 0x80000000u);
+            } else {
+              key[i] = 0ull;
+              pay[i] = 0u;
+            }
+          }
+          bitonic_desc<LPL, IPL, true>(key, pay, gl);
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) {
+            p[i] = (int)(pay[i] & 0x7FFFFFFFu);
+            if (pay[i] >> 31) inval |= (1u << i);
+          }
+        }
+      } else {
+        uint64_t key[IPL];
+        uint32_t nopay[IPL];
+        const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16,
+                            P.seed_lo, P.seed_hi};
+        int sel[IPL];
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) sel[i] = 0;
+        if (SRC == SRC_PHILOX) {
+#pragma unroll
+          for (int q = 0; q < IPL / 4; ++q) {
+            const int e0 = gl * IPL + q * 4;
+            if (e0 < K) {
+              const Philox4 r = ds.block((uint32_t)(e0 >> 2));
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (e0 + j < K) sel[q * 4 + j] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)(e0 + j));
+            }
+          }
+          if (P.sel_out != nullptr && active) {
+            int32_t* so = P.sel_out + list_id * K;
+#pragma unroll
+            for (int i = 0; i < IPL; ++i)
+              if (gl * IPL + i < K) so[gl * IPL + i] = sel[i];
+          }
+        } else {
+          const int32_t* __restrict__ sin = P.sel_in + list_id * K;
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) {
+            const int e = gl * IPL + i;
+            if (e < K) {
+              int s = __ldg(sin + e);
+              if (s < 0 || (uint32_t)s >= M) { bad |= PLD_ST_BAD_INDEX; s = 0; }
+              sel[i] = s;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          const int e = gl * IPL + i;
+          if (e < K) {
+            const int q = __ldg(vflat + sel[i]);
+            const float g = __ldg(gt + q);
+            key[i] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)e << 23) | (uint32_t)q;
+          } else {
+            key[i] = 0ull;
+          }
+        }
+        bitonic_desc<LPL, IPL, false>(key, nopay, gl);
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          p[i] = (int)((uint32_t)key[i] & 0x7FFFFFu);
+          lab[i] = ordered_to_float((uint32_t)(key[i] >> 32));
+        }
+        if (P.rank_out != nullptr && active) {
+          float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K;
+#pragma unroll
+          for (int i = 0; i < IPL; ++i)
+            if (gl * IPL + i < K) ro[gl * IPL + i] = make_float2((float)p[i], lab[i]);
+        }
+      }
+
+      if (LOSS) {
+        float s[IPL], ex[IPL], S[IPL];
+        float m = -3.402823466e38f;
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          const int e = gl * IPL + i;
+          s[i] = 0.f;
+          if (e < K) {
+            s[i] = ((inval >> i) & 1u) ? PLD_LOG_EPS : __ldg(pred + p[i]);
+            m = fmaxf(m, s[i]);
+          }
+        }
+        m = group_max<LPL>(m);
+        float run = 0.f;
+#pragma unroll
+        for (int i = IPL - 1; i >= 0; --i) {
+          ex[i] = (gl * IPL + i < K) ? expf(s[i] - m) : 0.f;
+          run += ex[i];
+          S[i] = run;
+        }
+        const float carry = group_excl_suffix<LPL>(run, gl);
+        float nll = 0.f, c = 0.f;
+        float cl[IPL];
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          cl[i] = 0.f;
+          if (gl * IPL + i < K) {
+            S[i] += carry;
+            nll += logf(S[i]) - (s[i] - m);
+            c += 1.0f / S[i];
+            cl[i] = c;
+          }
+        }
+        const float cpre = group_excl_prefix<LPL>(c, gl);
+        nll = group_sum<LPL>(nll);
+        if (active) {
+          if (gl == 0) {
+            local += nll;
+            if (P.per_list != nullptr) P.per_list[list_id] = nll;
+          }
+          if (P.grad != nullptr) {
+            float* gr = P.grad + map_off;
+#pragma unroll
+            for (int i = 0; i < IPL; ++i)
+              if (gl * IPL + i < K && !((inval >> i) & 1u))
+                atomicAdd(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
+          }
+        }
+      }
+    }
+  }
+  if (bad) atomicOr(P.status, bad);
+  if (LOSS) block_loss_epilogue(local, P.partials, P.ticket, P.scale, P.loss, P.loss_sum);
+}
+
+template <int LPL, int IPL>
+static int launch_large_cfg(const ListParams& P, int src, bool loss, dim3 grid, cudaStream_t st) {
+  if (src == SRC_PHILOX) {
+    if (loss) lists_large_kernel<LPL, IPL, SRC_PHILOX, true><<<grid, 256, 0, st>>>(P);
+    else lists_large_kernel<LPL, IPL, SRC_PHILOX, false><<<grid, 256, 0, st>>>(P);
+  } else if (src == SRC_FED_SEL) {
+    if (loss) lists_large_kernel<LPL, IPL, SRC_FED_SEL, true><<<grid, 256, 0, st>>>(P);
+    else lists_large_kernel<LPL, IPL, SRC_FED_SEL, false><<<grid, 256, 0, st>>>(P);
+  } else if (src == SRC_FED_RANK) {
+    lists_large_kernel<LPL, IPL, SRC_FED_RANK, true><<<grid, 256, 0, st>>>(P);
+  } else {
+    set_error("lists_large: bad source %d", src);
+    return PLD_EINVAL;
+  }
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st) {
+  const int K = P.K;
+  int lpl;
+  if (K <= 32) lpl = 4;
+  else if (K <= 64) lpl = 8;
+  else if (K <= 128) lpl = 16;
+  else lpl = 32;
+  const int gpb = 256 / lpl;
+  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  int gx = (P.n + gpb - 1) / gpb;
+  if (gx > per_image_cap) gx = per_image_cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)P.B);
+  if (K <= 32) return launch_large_cfg<4, 8>(P, src, loss, grid, st);
+  if (K <= 64) return launch_large_cfg<8, 8>(P, src, loss, grid, st);
+  if (K <= 128) return launch_large_cfg<16, 8>(P, src, loss, grid, st);
+  if (K <= 256) return launch_large_cfg<32, 8>(P, src, loss, grid, st);
+  if (K <= 512) return launch_large_cfg<32, 16>(P, src, loss, grid, st);
+  set_error("lists_large: K=%d out of range", K);
+  return PLD_EINVAL;
+}
+
+}  // namespace pld

@@ -1,0 +1,179 @@
+// Thread-per-list kernels for ranking_size K <= 16: draw / order / emit / ListMLE fwd+bwd.
+// One thread owns one list; all K entries live in registers.
+#include "pld_lists.cuh"
+
+namespace pld {
+
+template <int K, int SRC, bool LOSS>
+__global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
+  const int b = blockIdx.y;
+  const size_t map_off = (size_t)b * (size_t)P.HW;
+  const float* __restrict__ gt = P.gt + map_off;
+  const float* __restrict__ pred = P.pred + map_off;
+  float local = 0.f;
+  int bad = 0;
+
+  uint32_t M = 1, thresh = 0;
+  const int32_t* __restrict__ vflat = nullptr;
+  if (SRC != SRC_FED_RANK) {
+    const int m = P.n_valid[b];
+    if (m <= 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
+    else { M = (uint32_t)m; thresh = (0u - M) % M; }
+    vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
+  }
+
+  if (M != 0) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < P.n; l += gridDim.x * blockDim.x) {
+      const size_t list_id = (size_t)b * (size_t)P.n + (size_t)l;
+      int p[K];
+      float lab[K];
+      bool valid_all = true;
+      uint32_t inval = 0;  // bit k: sorted entry k has an invalid (negative) label
+
+      if (SRC == SRC_FED_RANK) {
+        const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) + list_id * K;
+        bool sorted = true;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float2 v = __ldg(rin + k);
+          int q = (int)v.x;  // tf.cast(point_coords, int32): truncation (depth_utils.py:50)
+          if (q < 0 || q >= P.HW) { bad |= PLD_ST_BAD_INDEX; q = 0; }
+          p[k] = q;
+          lab[k] = v.y;
+          valid_all = valid_all && (v.y >= 0.f);
+        }
+#pragma unroll
+        for (int k = 1; k < K; ++k) sorted = sorted && (lab[k - 1] >= lab[k]);
+        if (!(sorted && valid_all)) {
+          // TF-Ranking ordering: valid labels descending, invalid ones last with key
+          // min(labels') - 1e-6; ties keep the earlier position first (stable).
+          float mn = 3.402823466e38f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) mn = fminf(mn, lab[k] >= 0.f ? lab[k] : 0.f);
+          const float inv_key = mn - 1e-6f;
+          uint64_t key[K];
+          uint32_t pay[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const bool v = lab[k] >= 0.f;
+            const float kv = v ? lab[k] : inv_key;
+            key[k] = ((uint64_t)float_to_ordered(kv) << 32) | (uint32_t)(0xFFFF - k);
+            pay[k] = (uint32_t)p[k] | (v ? 0u : 0x80000000u);
+          }
+          sort_desc_regs<K, true>(key, pay);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            p[k] = (int)(pay[k] & 0x7FFFFFFFu);
+            if (pay[k] >> 31) inval |= (1u << k);
+          }
+        }
+      } else {
+        uint64_t key[K];
+        uint32_t nopay[K];
+        DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16, P.seed_lo,
+                      P.seed_hi};
+        int sel[K];
+        if (SRC == SRC_PHILOX) {
+#pragma unroll
+          for (int q = 0; q < (K + 3) / 4; ++q) {
+            const Philox4 r = ds.block((uint32_t)q);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = q * 4 + j;
+              if (k < K) sel[k] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)k);
+            }
+          }
+        } else {
+          const int32_t* __restrict__ sin = P.sel_in + list_id * K;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            int s = __ldg(sin + k);
+            if (s < 0 || (uint32_t)s >= M) { bad |= PLD_ST_BAD_INDEX; s = 0; }
+            sel[k] = s;
+          }
+        }
+        if (P.sel_out != nullptr && SRC == SRC_PHILOX) {
+          int32_t* so = P.sel_out + list_id * K;
+#pragma unroll
+          for (int k = 0; k < K; ++k) so[k] = sel[k];
+        }
+        int q[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) q[k] = __ldg(vflat + sel[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float g = __ldg(gt + q[k]);
+          key[k] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)k << 23) | (uint32_t)q[k];
+        }
+        sort_desc_regs<K, false>(key, nopay);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          p[k] = (int)((uint32_t)key[k] & 0x7FFFFFu);
+          lab[k] = ordered_to_float((uint32_t)(key[k] >> 32));
+        }
+        if (P.rank_out != nullptr) {
+          float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K;
+#pragma unroll
+          for (int k = 0; k < K; ++k) ro[k] = make_float2((float)p[k], lab[k]);
+        }
+      }
+
+      if (LOSS) {
+        float s[K], g[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] = __ldg(pred + p[k]);
+        if (inval) {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if ((inval >> k) & 1u) s[k] = PLD_LOG_EPS;
+        }
+        const float nll = listmle_regs<K>(s, g);
+        local += nll;
+        if (P.per_list != nullptr) P.per_list[list_id] = nll;
+        if (P.grad != nullptr) {
+          float* gr = P.grad + map_off;
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (!((inval >> k) & 1u)) atomicAdd(gr + p[k], g[k] * P.scale);
+        }
+      }
+    }
+  }
+  if (bad) atomicOr(P.status, bad);
+  if (LOSS) block_loss_epilogue(local, P.partials, P.ticket, P.scale, P.loss, P.loss_sum);
+}
+
+template <int SRC, bool LOSS>
+static int launch_small_k(const ListParams& P, dim3 grid, cudaStream_t st) {
+  switch (P.K) {
+#define PLD_CASE(KK)                                               \
+  case KK:                                                         \
+    lists_small_kernel<KK, SRC, LOSS><<<grid, 256, 0, st>>>(P);    \
+    break;
+    PLD_CASE(1) PLD_CASE(2) PLD_CASE(3) PLD_CASE(4) PLD_CASE(5) PLD_CASE(6) PLD_CASE(7) PLD_CASE(8)
+    PLD_CASE(9) PLD_CASE(10) PLD_CASE(11) PLD_CASE(12) PLD_CASE(13) PLD_CASE(14) PLD_CASE(15)
+    PLD_CASE(16)
+#undef PLD_CASE
+    default:
+      set_error("lists_small: K=%d out of range", P.K);
+      return PLD_EINVAL;
+  }
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st) {
+  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  int gx = (P.n + 255) / 256;
+  if (gx > per_image_cap) gx = per_image_cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)P.B);
+  if (src == SRC_PHILOX) return loss ? launch_small_k<SRC_PHILOX, true>(P, grid, st) : launch_small_k<SRC_PHILOX, false>(P, grid, st);
+  if (src == SRC_FED_SEL) return loss ? launch_small_k<SRC_FED_SEL, true>(P, grid, st) : launch_small_k<SRC_FED_SEL, false>(P, grid, st);
+  if (src == SRC_FED_RANK) return launch_small_k<SRC_FED_RANK, true>(P, grid, st);
+  set_error("lists_small: bad source %d", src);
+  return PLD_EINVAL;
+}
+
+}  // namespace pld

@@ -1,0 +1,96 @@
+"""Keras-signature ListMLE / Plackett-Luce loss on the fused CUDA kernel.
+
+Mirror of pldepth/losses/nll_loss.py:32-62 (``HourglassNegativeLogLikelihood`` ->
+``FullyFledgedMetaBatchListMLELoss`` -> TF-Ranking 0.3.1 ``ListMLELoss``) with the reshape /
+gather contract of pldepth/data/depth_utils.py:39-61:
+
+    loss = HourglassNegativeLogLikelihood(ranking_size=K, batch_size=B)
+    value = loss(y_true, y_pred)      # y_true (B,R,K,2) f32, y_pred (B,H,W,1)|(B,H,W) f32
+    value.backward()                  # d value / d y_pred, dense, duplicates accumulated
+
+R is inferred from y_true (depth_utils.py:43) so train / validation R may differ
+(nll_loss.py:58).  Forward and backward are ONE kernel launch: the gradient is produced
+together with the loss and handed to autograd.
+"""
+import torch
+
+from . import ops
+
+_REDUCTIONS = ("auto", "sum_over_batch_size", "sum", "none")
+
+
+class _ListMLEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, batch_size, ranking_size, reduction, global_lists):
+        R = y_true.numel() // (batch_size * ranking_size * 2)
+        L = batch_size * R
+        if reduction in ("auto", "sum_over_batch_size"):
+            scale = 1.0 / float(global_lists if global_lists else L)
+        else:
+            scale = 1.0
+        need_grad = y_pred.requires_grad
+        want_pl = reduction == "none"
+        if want_pl and need_grad:
+            raise NotImplementedError("reduction='none' is forward-only (per-list NLL); reduce before backward")
+        loss, loss_sum, grad, per_list = ops.listmle_fwd_bwd(y_true, y_pred.detach(), batch_size, ranking_size,
+                                                             scale, want_grad=need_grad, want_per_list=want_pl)
+        ctx.has_grad = need_grad
+        if need_grad:
+            ctx.save_for_backward(grad)
+        ctx.pred_shape = y_pred.shape
+        ctx.pred_dtype = y_pred.dtype
+        if want_pl:
+            return per_list.reshape(L, 1)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if not ctx.has_grad:
+            return None, None, None, None, None, None
+        (g,) = ctx.saved_tensors
+        g = g.reshape(ctx.pred_shape) * grad_output
+        return g.to(ctx.pred_dtype), None, None, None, None, None
+
+
+class HourglassNegativeLogLikelihood(object):
+    """Drop-in for pldepth/losses/nll_loss.py:32-40 (constructor arguments identical).
+
+    ``reduction``: 'auto' / 'sum_over_batch_size' (Keras AUTO, mean over the B*R lists --
+    what every reference script uses), 'sum', or 'none' (per-list NLL ``(L, 1)``, forward only).
+    ``lambda_weight`` must be None (every call site in the reference passes None).
+    ``global_lists`` (extension): total number of lists across all data-parallel ranks, so a
+    shard's loss / gradient carry the global 1/L factor (see pldepth_b200.dist).
+    """
+
+    def __init__(self, ranking_size, batch_size, reduction="auto", name=None, lambda_weight=None,
+                 debug=False, global_lists=None):
+        red = getattr(reduction, "name", reduction)   # accept tf.losses.Reduction members
+        red = str(red).lower()
+        if red not in _REDUCTIONS:
+            raise ValueError("unsupported reduction %r" % (reduction,))
+        if lambda_weight is not None:
+            raise NotImplementedError("lambda_weight is not used anywhere in the reference; only None is supported")
+        if int(ranking_size) < 1 or int(ranking_size) > 512:
+            raise ValueError("ranking_size must be in [1, 512]")
+        self.ranking_size = int(ranking_size)
+        self.batch_size = int(batch_size)
+        self.reduction = red
+        self.name = name
+        self.debug = debug
+        self.global_lists = global_lists
+
+    def __call__(self, y_true, y_pred, sample_weight=None):
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is never passed by the reference")
+        if not isinstance(y_pred, torch.Tensor):
+            y_pred = torch.from_dlpack(y_pred)
+        if not isinstance(y_true, torch.Tensor):
+            y_true = torch.from_dlpack(y_true)
+        if self.debug:
+            print("point_coords:", y_true.reshape(self.batch_size, -1, self.ranking_size, 2)[..., 0].flatten()[:10])
+        return _ListMLEFunction.apply(y_pred, y_true, self.batch_size, self.ranking_size, self.reduction,
+                                      self.global_lists)
+
+    def get_config(self):
+        return {"ranking_size": self.ranking_size, "batch_size": self.batch_size, "reduction": self.reduction,
+                "name": self.name}

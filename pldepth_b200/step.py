@@ -1,0 +1,81 @@
+"""The fused hot-path step as one object: valid-pixel table -> Philox sampling -> gather ->
+ListMLE forward + backward, for a batch of images resident on one GPU.
+
+This is what replaces, per training step, the reference's tf.data sampler map
+(hourglass_provider.py:55-62), ``prepare_fully_fledged_loss_input`` (depth_utils.py:39-61) and the
+TF-Ranking ListMLE loss + its autodiff (nll_loss.py:32-62).  Output buffers are preallocated and
+reused, so a step is three kernel launches and one memset on the current stream, no host sync.
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import Context, check, c_void_p
+
+
+class FusedPLStep(object):
+    def __init__(self, ranking_size, rankings_per_image, seed=0, emit_rankings=True, global_batch=None,
+                 image_base=0):
+        self.K = int(ranking_size)
+        self.R = int(rankings_per_image)
+        self.seed = int(seed)
+        self.emit_rankings = bool(emit_rankings)
+        self.global_batch = global_batch
+        self.image_base = int(image_base)
+        self.step_index = 0
+        self._buf = None
+
+    def _buffers(self, B, H, W, Hm, Wm, dev):
+        key = (B, H, W, Hm, Wm, dev)
+        if self._buf is None or self._buf["key"] != key:
+            self._buf = dict(
+                key=key,
+                valid_flat=torch.empty((B, Hm * Wm), dtype=torch.int32, device=dev),
+                n_valid=torch.empty((B,), dtype=torch.int32, device=dev),
+                rankings=(torch.empty((B, self.R, self.K, 2), dtype=torch.float32, device=dev)
+                          if self.emit_rankings else None),
+                grad=torch.empty((B, H, W, 1), dtype=torch.float32, device=dev),
+                loss=torch.empty(1, dtype=torch.float32, device=dev),
+                loss_sum=torch.empty(1, dtype=torch.float64, device=dev),
+            )
+        return self._buf
+
+    def run(self, gt, mask, pred, out=None):
+        """gt f32[B,H,W], mask f32[B,Hm,Wm], pred f32[B,H,W(,1)] on one CUDA device.
+        Returns dict(loss f32[1], loss_sum f64[1], grad f32[B,H,W,1], rankings f32[B,R,K,2]|None).
+        ``loss`` carries the factor 1/(global_batch*R) (global_batch defaults to B)."""
+        dev = gt.device
+        B, H, W = gt.shape[0], gt.shape[1], gt.shape[2]
+        Hm, Wm = mask.shape[1], mask.shape[2]
+        buf = out if out is not None else self._buffers(B, H, W, Hm, Wm, dev)
+        ctx = Context.current(dev.index or 0)
+        lib = ctx.lib
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        gb = self.global_batch if self.global_batch else B
+        scale = 1.0 / (float(gb) * float(self.R))
+        p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+        check(lib.pld_mask_compact(ctx.handle, p(mask), B, Hm, Wm, H, W, p(buf["valid_flat"]), p(buf["n_valid"]),
+                                   stream))
+        check(lib.pld_fused_sample_loss_bwd(ctx.handle, p(gt), p(buf["valid_flat"]), p(buf["n_valid"]), p(pred), B,
+                                            H * W, Hm * Wm, self.K, self.R, self.seed, self.step_index,
+                                            self.image_base, ctypes.c_float(scale), p(buf["rankings"]),
+                                            p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None), p(buf["grad"]), 0,
+                                            stream))
+        self.step_index += 1
+        return buf
+
+    @staticmethod
+    def new_buffers(B, H, W, Hm, Wm, R, K, dev, emit_rankings=True):
+        return dict(
+            key=None,
+            valid_flat=torch.empty((B, Hm * Wm), dtype=torch.int32, device=dev),
+            n_valid=torch.empty((B,), dtype=torch.int32, device=dev),
+            rankings=torch.empty((B, R, K, 2), dtype=torch.float32, device=dev) if emit_rankings else None,
+            grad=torch.empty((B, H, W, 1), dtype=torch.float32, device=dev),
+            loss=torch.empty(1, dtype=torch.float32, device=dev),
+            loss_sum=torch.empty(1, dtype=torch.float64, device=dev),
+        )
+
+    def check(self, dev):
+        return ops.check_status(dev)

@@ -1,0 +1,188 @@
+"""GPU parity tests, stages 2-3 (gather + ListMLE NLL + gradient scatter-add) and the fused
+step, through the C ABI.  Tolerance: 1e-5 relative (BASELINE.json north_star), measured on the
+loss and on the gradient map in the max norm relative to the largest gradient entry."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import listmle_oracle as lo
+from oracle import sampler_oracle as so
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def make_problem(B, H, W, K, R, seed, sorted_lists=True, dup=True):
+    rs = np.random.RandomState(seed)
+    pred = (rs.randn(B, H, W, 1) * 1.5).astype(np.float32)
+    idx = rs.randint(0, H * W, size=(B, R, K))
+    if dup and K >= 2:
+        idx[:, 0, 1] = idx[:, 0, 0]
+    depth = rs.permutation(B * R * K).reshape(B, R, K).astype(np.float64)
+    depth = (depth + 0.5) / (B * R * K)
+    if sorted_lists:
+        depth = np.sort(depth, axis=2)[:, :, ::-1]
+    y_true = np.stack([idx.astype(np.float32), depth.astype(np.float32)], axis=-1)
+    return y_true, pred
+
+
+def assert_close(got, want, what):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    denom = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / denom
+    assert err <= RTOL, "%s: relative error %.3e > %.1e" % (what, err, RTOL)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 8, 10, 16, 17, 32, 50, 64, 100, 128, 250, 256, 500, 512])
+@pytest.mark.parametrize("sorted_lists", [True, False])
+def test_loss_and_gradient_match_oracle(cuda_device, K, sorted_lists):
+    from pldepth_b200 import ops
+    B, H, W = 3, 24, 20
+    R = 130 if K <= 64 else 19
+    y_true, pred = make_problem(B, H, W, K, R, 10 * K + sorted_lists, sorted_lists)
+    want_loss, want_grad, want_pl = lo.hourglass_nll(y_true, pred, B, K)
+    loss, loss_sum, grad, per_list = ops.listmle_fwd_bwd(torch.from_numpy(y_true).to(cuda_device),
+                                                         torch.from_numpy(pred).to(cuda_device), B, K,
+                                                         1.0 / (B * R), want_grad=True, want_per_list=True)
+    ops.check_status(cuda_device)
+    assert_close(loss.item(), want_loss, "loss")
+    assert_close(loss_sum.item(), want_pl.sum(), "loss_sum")
+    assert_close(per_list.cpu().numpy(), want_pl, "per-list NLL")
+    assert grad.shape == pred.shape
+    assert_close(grad.cpu().numpy(), want_grad, "gradient")
+
+
+def test_known_answer_through_keras_signature(cuda_device):
+    from pldepth_b200.losses import HourglassNegativeLogLikelihood
+    # two lists on a 1x3 map: scores (0, ln3, ln2); orders (1,2,0) and (2,0,1)
+    pred = torch.tensor([[[[0.0], [np.log(3.0)], [np.log(2.0)]]]], dtype=torch.float32, device=cuda_device,
+                        requires_grad=True)
+    y_true = torch.tensor([[[[1, 0.9], [2, 0.5], [0, 0.1]], [[2, 0.9], [0, 0.5], [1, 0.1]]]], dtype=torch.float32,
+                          device=cuda_device)
+    loss_fn = HourglassNegativeLogLikelihood(ranking_size=3, batch_size=1)
+    val = loss_fn(y_true, pred)
+    # list 1: P = 3/6 * 2/3 -> nll = ln2 + ln1.5 ; list 2: P = 2/6 * 1/4 -> nll = ln3 + ln4
+    want = 0.5 * ((np.log(2) + np.log(1.5)) + (np.log(3) + np.log(4)))
+    assert abs(val.item() - want) < 1e-6
+    val.backward()
+    assert abs(pred.grad.sum().item()) < 1e-6
+
+
+def test_invalid_labels_and_ties(cuda_device):
+    from pldepth_b200 import ops
+    B, H, W, K, R = 2, 10, 10, 6, 50
+    y_true, pred = make_problem(B, H, W, K, R, 5, sorted_lists=False)
+    rs = np.random.RandomState(0)
+    neg = rs.rand(B, R, K) < 0.2
+    y_true[..., 1][neg] = -1.0
+    y_true[:, 1, 2, 1] = y_true[:, 1, 4, 1] = 0.5        # a tie between valid labels (stable rule)
+    y_true[:, 3, :, 1] = -2.0                            # a list with no valid label at all
+    want_loss, want_grad, want_pl = lo.hourglass_nll(y_true, pred, B, K)
+    loss, _, grad, per_list = ops.listmle_fwd_bwd(torch.from_numpy(y_true).to(cuda_device),
+                                                  torch.from_numpy(pred).to(cuda_device), B, K, 1.0 / (B * R),
+                                                  want_per_list=True)
+    assert_close(per_list.cpu().numpy(), want_pl, "per-list NLL")
+    assert_close(loss.item(), want_loss, "loss")
+    assert_close(grad.cpu().numpy(), want_grad, "gradient")
+
+
+def test_bad_index_raises(cuda_device):
+    from pldepth_b200 import ops
+    y_true, pred = make_problem(1, 4, 4, 3, 5, 1)
+    y_true[0, 2, 1, 0] = 16.0
+    ops.listmle_fwd_bwd(torch.from_numpy(y_true).to(cuda_device), torch.from_numpy(pred).to(cuda_device), 1, 3, 1.0)
+    with pytest.raises(IndexError):
+        ops.check_status(cuda_device)
+
+
+def test_reductions_autograd_and_validation_R(cuda_device):
+    from pldepth_b200.losses import HourglassNegativeLogLikelihood
+    B, H, W, K = 2, 12, 12, 5
+    for R in (7, 30):                                   # R is inferred per call (nll_loss.py:58)
+        y_true, pred = make_problem(B, H, W, K, R, R)
+        yt = torch.from_numpy(y_true).to(cuda_device)
+        for red, factor in (("auto", 1.0), ("sum", float(B * R))):
+            p = torch.from_numpy(pred).to(cuda_device).requires_grad_(True)
+            fn = HourglassNegativeLogLikelihood(K, B, reduction=red)
+            v = fn(yt, p)
+            (v * 3.0).backward()
+            want_loss, want_grad, want_pl = lo.hourglass_nll(y_true, pred, B, K, reduction=red)
+            assert_close(v.item(), want_loss, "loss " + red)
+            assert_close(p.grad.cpu().numpy(), 3.0 * want_grad, "grad " + red)
+        none = HourglassNegativeLogLikelihood(K, B, reduction="none")(yt, torch.from_numpy(pred).to(cuda_device))
+        assert none.shape == (B * R, 1)
+        assert_close(none.cpu().numpy()[:, 0], want_pl, "per-list")
+    with pytest.raises(NotImplementedError):
+        HourglassNegativeLogLikelihood(K, B, lambda_weight=object())
+
+
+@pytest.mark.parametrize("K,n", [(5, 1000), (10, 300), (50, 100), (200, 20)])
+def test_fused_equals_sample_then_loss(cuda_device, K, n):
+    """Fused step == Philox sampling followed by the loss on its rankings; both == oracle."""
+    from pldepth_b200 import ops
+    from tests.test_gpu_sampler import make_maps
+    B, H, W = 3, 36, 44
+    gt, mask = make_maps(H, W, H, W, K, B)
+    pred = np.random.RandomState(K).randn(B, H, W, 1).astype(np.float32)
+    gt_d, pred_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    loss, loss_sum, grad, rank, per_list = ops.fused_sample_loss_bwd(gt_d, vf, nv, pred_d, K, n, seed=77, offset=3,
+                                                                     want_per_list=True)
+    rank2, _ = ops.sample_lists_philox(gt_d, vf, nv, K, n, 77, 3, 0)
+    assert torch.equal(rank, rank2)
+    loss2, _, grad2, pl2 = ops.listmle_fwd_bwd(rank2, pred_d, B, K, 1.0 / (B * n), want_per_list=True)
+    assert torch.equal(per_list, pl2)
+    assert abs(loss.item() - loss2.item()) <= 1e-6 * abs(loss2.item())
+    assert_close(grad.cpu().numpy(), grad2.cpu().numpy(), "fused vs two-step gradient")
+    want_loss, want_grad, _ = lo.hourglass_nll(rank.cpu().numpy(), pred, B, K)
+    assert_close(loss.item(), want_loss, "loss")
+    assert_close(grad.cpu().numpy(), want_grad, "gradient")
+    # forward-only and no-rankings variants
+    l3, _, g3, r3, _ = ops.fused_sample_loss_bwd(gt_d, vf, nv, pred_d, K, n, seed=77, offset=3, want_rankings=False,
+                                                 want_grad=False)
+    assert g3 is None and r3 is None and l3.item() == loss.item()
+
+
+def test_loss_is_deterministic(cuda_device):
+    from pldepth_b200 import ops
+    y_true, pred = make_problem(4, 64, 64, 5, 5000, 3)
+    yt, p = torch.from_numpy(y_true).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    vals = {ops.listmle_fwd_bwd(yt, p, 4, 5, 1.0 / 20000, want_grad=False)[0].item() for _ in range(5)}
+    assert len(vals) == 1
+
+
+def test_full_size_config2_properties(cuda_device):
+    """BASELINE config 2 (B32, 448^2, K5, R100k) at full size: size-independent properties --
+    lists depth-descending with in-range indices, per-list gradients sum to zero so the dense
+    gradient sums to ~0, loss equals the mean of the per-list NLL, and a 2k-list sample of the
+    emitted rankings reproduces the oracle's per-list NLL."""
+    from pldepth_b200 import ops, synth
+    B, H, W, K, R = 32, 448, 448, 5, 100000
+    rs = np.random.RandomState(0)
+    gt1 = synth.depth_map(H, W, 2000)
+    gt = np.stack([np.roll(gt1, 37 * b, axis=1) for b in range(B)])
+    mask = np.ones((B, H, W), np.float32)
+    mask[:, 100:160, 50:300] = 0
+    pred = rs.standard_normal((B, H, W, 1)).astype(np.float32)
+    gt_d, pred_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    loss, loss_sum, grad, rank, per_list = ops.fused_sample_loss_bwd(gt_d, vf, nv, pred_d, K, R, seed=2, offset=0,
+                                                                     want_per_list=True)
+    ops.check_status(cuda_device)
+    assert int(nv[0].item()) == H * W - 60 * 250
+    d = rank[..., 1]
+    assert bool((d[:, :, :-1] >= d[:, :, 1:]).all())
+    idx = rank[..., 0].long()
+    assert int(idx.min()) >= 0 and int(idx.max()) < H * W
+    rows, cols = idx // W, idx % W
+    assert not bool(((rows >= 100) & (rows < 160) & (cols >= 50) & (cols < 300)).any())   # masked pixels never drawn
+    assert bool((torch.gather(gt_d.reshape(B, -1), 1, idx.reshape(B, -1)).reshape(B, R, K) == d).all())
+    assert abs(loss.item() - per_list.double().mean().item()) <= 1e-6 * abs(loss.item())
+    gsum = grad.double().sum().item()
+    gabs = grad.double().abs().sum().item()
+    assert abs(gsum) <= 1e-5 * gabs
+    pick = rs.randint(0, R, size=2000)
+    sub = rank[5, pick].cpu().numpy()[None]
+    _, _, want_pl = lo.hourglass_nll(sub, pred[5:6], 1, K)
+    assert_close(per_list.reshape(B, R)[5, pick].cpu().numpy(), want_pl, "per-list NLL at full size")

@@ -1,0 +1,186 @@
+"""GPU parity tests, stage 1 (sampler), through the C ABI.  Bit-exact against the oracle and
+against the reference's golden outputs (tests/golden)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mt19937_oracle as mto
+from oracle import sampler_oracle as so
+from tests import philox_model as pm
+from tests.test_oracle_sampler import CLS2STRAT, load_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sampler_*.npz")))
+
+
+def make_maps(H, W, Hm, Wm, seed, B=2, hole=True):
+    rs = np.random.RandomState(seed)
+    gt = np.stack([((rs.permutation(H * W) + 0.5) / (H * W)).astype(np.float32).reshape(H, W) for _ in range(B)])
+    mask = (rs.rand(B, Hm, Wm) > (0.25 if hole else -1)).astype(np.float32)
+    return gt, mask
+
+
+@pytest.mark.parametrize("H,W,Hm,Wm", [(24, 32, 24, 32), (24, 32, 12, 8), (30, 20, 7, 9), (448, 448, 448, 448),
+                                       (65, 67, 65, 67)])
+def test_mask_compact_matches_np_where(cuda_device, H, W, Hm, Wm):
+    from pldepth_b200 import ops
+    gt, mask = make_maps(H, W, Hm, Wm, 1, B=3)
+    mask[1] = 1.0                       # a full mask
+    mask[2, :, :] = 0
+    mask[2, Hm - 1, Wm - 1] = 0.5       # a single valid pixel
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    vf, nv = vf.cpu().numpy(), nv.cpu().numpy()
+    for b in range(3):
+        want = so.valid_flat_indices(mask[b], (H, W))
+        assert nv[b] == want.shape[0]
+        assert np.array_equal(vf[b, :nv[b]], want)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 8, 10, 16, 17, 31, 32, 50, 64, 100, 128, 200, 256, 500, 512])
+def test_philox_draws_and_rankings(cuda_device, K):
+    """Philox mode: the draws equal the independent NumPy Philox model, and the rankings equal
+    the oracle fed with those draws ("same fed indices" parity)."""
+    from pldepth_b200 import ops
+    H, W = 40, 50
+    B = 2
+    n = 257 if K <= 64 else 41
+    gt, mask = make_maps(H, W, H, W, 100 + K, B)
+    gt_d = torch.from_numpy(gt).to(cuda_device)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    seed, offset, base = 0x1234_5678_9ABC, 7 + (3 << 32), 5
+    rank, sel = ops.sample_lists_philox(gt_d, vf, nv, K, n, seed, offset, base, want_sel=True)
+    ops.check_status(cuda_device)
+    rank, sel, nvh = rank.cpu().numpy(), sel.cpu().numpy(), nv.cpu().numpy()
+    for b in range(B):
+        want_sel = pm.draw_selection(seed, offset, base + b, n, K, int(nvh[b]))
+        assert np.array_equal(sel[b], want_sel)
+        want = so.rankings_from_selection(sel[b].reshape(-1), so.valid_flat_indices(mask[b], (H, W)), gt[b], K)
+        assert np.array_equal(rank[b], want)
+
+
+def test_philox_is_independent_of_batch_split(cuda_device):
+    from pldepth_b200 import ops
+    H, W, K, n = 32, 32, 5, 300
+    gt, mask = make_maps(H, W, H, W, 3, B=4)
+    gt_d, mask_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(mask).to(cuda_device)
+    vf, nv = ops.mask_compact(mask_d, H, W)
+    full, _ = ops.sample_lists_philox(gt_d, vf, nv, K, n, 42, 1, 0)
+    vf2, nv2 = ops.mask_compact(mask_d[2:], H, W)
+    part, _ = ops.sample_lists_philox(gt_d[2:], vf2, nv2, K, n, 42, 1, 2)
+    assert torch.equal(full[2:], part)
+
+
+@pytest.mark.parametrize("K", [4, 5, 16, 20, 64])
+def test_ties_later_draw_first(cuda_device, K):
+    """Heavily tied depths: same rule as the oracle (reversed stable argsort)."""
+    from pldepth_b200 import ops
+    H, W, n = 16, 16, 200
+    rs = np.random.RandomState(K)
+    gt = (rs.randint(0, 4, size=(1, H, W)) / 4).astype(np.float32)
+    mask = np.ones((1, H, W), np.float32)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    sel = rs.randint(0, H * W, size=(1, n, K)).astype(np.int32)
+    rank = ops.sample_lists_fed(torch.from_numpy(gt).to(cuda_device), vf, nv, K, torch.from_numpy(sel).to(cuda_device))
+    want = so.rankings_from_selection(sel.reshape(-1), np.arange(H * W), gt[0], K)
+    assert np.array_equal(rank[0].cpu().numpy(), want)
+
+
+def test_device_mt19937_equals_numpy(cuda_device):
+    from pldepth_b200 import ops
+    for seed in (0, 3, 2 ** 32 - 1):
+        state, pos = ops.mt19937_init(seed, cuda_device)
+        assert np.array_equal(state.cpu().numpy().view(np.uint32), mto.init_genrand(seed))
+        rs = np.random.RandomState(seed)
+        for n in (1, 623, 624, 625, 5000):
+            got = ops.mt19937_generate(state, pos, n).cpu().numpy().view(np.uint32)
+            want = rs.randint(0, 2 ** 32, size=n, dtype=np.uint32)
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[8:-4] for p in GOLDEN])
+@pytest.mark.parametrize("rng", ["numpy", "mt19937"])
+def test_sampler_classes_reproduce_reference_goldens(cuda_device, path, rng):
+    """The drop-in classes, fed like the reference (NumPy image/mask/gt), reproduce the
+    reference's own outputs bit for bit, and leave np.random in the same state."""
+    from pldepth_b200 import sampling
+    from pldepth_b200.models_meta import ModelParameters
+    c = load_case(path)
+    cls = {v: k for k, v in CLS2STRAT.items()}[c["strategy"]]
+    strat = getattr(sampling, cls)(ModelParameters(ranking_size=c["K"]), rng=rng, seed=c["seed"])
+    H, W = c["gt"].shape
+    image = np.zeros((H, W, 3), np.float32)
+    np.random.seed(c["seed"])
+    st0 = np.random.get_state()
+    if c["factor"] < 0:
+        out = strat.sample_masked_point_batch(image, c["mask"], c["gt"], c["R"])
+    elif c["strategy"] == "purely":
+        out, dists = strat.sample_masked_rankings(image, c["mask"], c["gt"], c["R"], c["factor"])
+        assert dists.shape == (out.shape[0],)
+    else:
+        out = strat.sample_masked_point_batch(image, c["mask"], c["gt"], c["R"], c["factor"])
+    assert out.dtype == np.float32
+    assert np.array_equal(out, c["rankings"])
+    if rng == "numpy":
+        st1 = np.random.get_state()
+        rs = np.random.RandomState()
+        rs.set_state(st0)
+        rs.randint(0, 2 ** 32, size=c["consumed"], dtype=np.uint32)
+        st2 = rs.get_state()
+        assert np.array_equal(st1[1], st2[1]) and st1[2] == st2[2]
+
+
+@pytest.mark.parametrize("strategy", ["masked", "thresholded", "information"])
+@pytest.mark.parametrize("promotion", ["nep50", "legacy"])
+@pytest.mark.parametrize("K", [2, 5, 7, 8, 9, 20, 130, 300])
+def test_scores_and_selection_match_oracle(cuda_device, strategy, promotion, K):
+    from pldepth_b200 import ops
+    from tests.golden.make_golden import near_threshold_gt
+    H, W, B, n, R = 48, 40, 3, 500, 333
+    rs = np.random.RandomState(K)
+    gt = np.stack([near_threshold_gt(H, W, 7 * K + b) for b in range(B)])
+    mask = np.ones((B, H, W), np.float32)
+    sel = rs.randint(0, H * W, size=(B, n, K)).astype(np.int32)
+    gt_d = torch.from_numpy(gt).to(cuda_device)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    cand = ops.sample_lists_fed(gt_d, vf, nv, K, torch.from_numpy(sel).to(cuda_device))
+    mm = ops.gt_minmax(gt_d) if strategy == "information" else None
+    scores = ops.score_lists(cand, strategy, 0.03, -1000, promotion, mm)
+    top, order = ops.select_top(scores, cand, R, want_order=True)
+    cand_h, scores_h, top_h, order_h = cand.cpu().numpy(), scores.cpu().numpy(), top.cpu().numpy(), order.cpu().numpy()
+    for b in range(B):
+        if strategy == "information":
+            want = so.score_information(cand_h[b], gt[b], 0.03, -1000, promotion)
+        else:
+            want = so.score_adjacent_differences(cand_h[b], 0.03 if strategy == "thresholded" else None, -1000,
+                                                 promotion)
+        assert np.array_equal(scores_h[b], want), (np.abs(scores_h[b] - want).max())
+        want_top, want_order = so.select_top(cand_h[b], want, R)
+        assert np.array_equal(order_h[b], want_order)
+        assert np.array_equal(top_h[b], want_top)
+
+
+def test_empty_mask_raises_like_randint0(cuda_device):
+    from pldepth_b200 import sampling
+    from pldepth_b200.models_meta import ModelParameters
+    strat = sampling.PurelyMaskedRandomSamplingStrategy(ModelParameters(ranking_size=3), rng="philox")
+    image = np.zeros((8, 8, 3), np.float32)
+    with pytest.raises(ValueError):
+        strat.sample_masked_point_batch(image, np.zeros((8, 8), np.float32), np.ones((8, 8), np.float32), 10)
+
+
+def test_single_valid_pixel_consumes_no_words(cuda_device):
+    from pldepth_b200 import sampling
+    from pldepth_b200.models_meta import ModelParameters
+    strat = sampling.PurelyMaskedRandomSamplingStrategy(ModelParameters(ranking_size=3), rng="numpy")
+    mask = np.zeros((8, 8), np.float32)
+    mask[2, 5] = 1
+    gt = np.random.RandomState(0).rand(8, 8).astype(np.float32)
+    np.random.seed(4)
+    st0 = np.random.get_state()
+    out = strat.sample_masked_point_batch(np.zeros((8, 8, 3)), mask, gt, 10)
+    st1 = np.random.get_state()
+    assert out.shape == (8, 3, 2) and (out[:, :, 0] == 21).all() and (out[:, :, 1] == gt[2, 5]).all()
+    assert np.array_equal(st0[1], st1[1]) and st0[2] == st1[2]

@@ -1,0 +1,251 @@
+// Micro-benchmarks that decide the memory staging of the PLDepth hot path on B200:
+// random 4/8/16-byte gathers and float atomic adds against (a) L2-resident global maps,
+// (b) this CTA's shared memory, (c) distributed shared memory of an 8-CTA cluster,
+// plus Philox4x32-10 issue rate.  Prints one JSON line per test.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+namespace cg = cooperative_groups;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ uint32_t xs32(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+
+constexpr int ITERS = 64;      // outer iterations per thread
+constexpr int UNR = 8;         // independent ops per iteration
+
+// ---- global gathers: block works inside an "image" region of region_words words ------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_global(const T* __restrict__ table, uint32_t region_elems,
+                                                       uint32_t n_regions, float* out) {
+  const T* base = table + (size_t)(blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+    uint32_t idx[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) idx[u] = __umulhi(xs32(s), region_elems);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      T v = __ldg(base + idx[u]);
+      acc += *reinterpret_cast<float*>(&v);
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_red_global(float* __restrict__ map, uint32_t region_elems,
+                                                    uint32_t n_regions) {
+  float* base = map + (size_t)(blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 777u;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) atomicAdd(base + __umulhi(xs32(s), region_elems), 1.0f);
+  }
+}
+
+// ---- shared memory --------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_smem(uint32_t elems, float* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  for (uint32_t i = threadIdx.x; i < elems * (sizeof(T) / 4); i += 256) reinterpret_cast<float*>(sm)[i] = (float)i;
+  __syncthreads();
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 99u;
+  float acc = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      T v = sm[__umulhi(xs32(s), elems)];
+      acc += *reinterpret_cast<float*>(&v);
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_atomic_smem(uint32_t elems, float* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  for (uint32_t i = threadIdx.x; i < elems; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 5u;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) atomicAdd(sm + __umulhi(xs32(s), elems), 1.0f);
+  }
+  __syncthreads();
+  if (sm[threadIdx.x] == 123.456f) out[0] = sm[threadIdx.x];
+}
+
+// ---- distributed shared memory (cluster) ------------------------------------------------------
+template <typename T, int CL>
+__global__ void __launch_bounds__(256) k_gather_dsmem(uint32_t elems, float* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  for (uint32_t i = threadIdx.x; i < elems * (sizeof(T) / 4); i += 256) reinterpret_cast<float*>(sm)[i] = (float)i;
+  cluster.sync();
+  const T* peers[CL];
+#pragma unroll
+  for (int r = 0; r < CL; ++r) peers[r] = cluster.map_shared_rank(sm, r);
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 31u;
+  float acc = 0.f;
+  const T* flat0 = peers[0];
+  const size_t stride = (const char*)peers[1 % CL] - (const char*)peers[0];
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      uint32_t r = xs32(s);
+      uint32_t rank = r & (CL - 1);
+      uint32_t idx = __umulhi(r * 2246822519u, elems);
+      const T* p = reinterpret_cast<const T*>((const char*)flat0 + (size_t)rank * stride) + idx;
+      T v = *p;
+      acc += *reinterpret_cast<float*>(&v);
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+  cluster.sync();
+}
+
+template <int CL>
+__global__ void __launch_bounds__(256) k_red_dsmem(uint32_t elems, float* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  for (uint32_t i = threadIdx.x; i < elems; i += 256) sm[i] = 0.f;
+  cluster.sync();
+  float* p0 = cluster.map_shared_rank(sm, 0);
+  float* p1 = cluster.map_shared_rank(sm, 1 % CL);
+  const size_t stride = (char*)p1 - (char*)p0;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 63u;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      uint32_t r = xs32(s);
+      uint32_t rank = r & (CL - 1);
+      uint32_t idx = __umulhi(r * 2246822519u, elems);
+      atomicAdd(reinterpret_cast<float*>((char*)p0 + (size_t)rank * stride) + idx, 1.0f);
+    }
+  }
+  cluster.sync();
+  if (sm[threadIdx.x] == 123.456f) out[0] = sm[threadIdx.x];
+}
+
+// ---- philox -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_philox(float* out) {
+  uint32_t c0 = blockIdx.x * 256 + threadIdx.x, acc = 0;
+  for (int it = 0; it < ITERS * UNR; ++it) {
+    uint32_t a = c0, b = it, c = 0, d = 0, k0 = 1, k1 = 2;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, a), lo0 = 0xD2511F53u * a;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c), lo1 = 0xCD9E8D57u * c;
+      a = hi1 ^ b ^ k0; b = lo1; c = hi0 ^ d ^ k1; d = lo0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    acc ^= a ^ b ^ c ^ d;
+  }
+  if (acc == 0x12345u) out[0] = 1.f;
+}
+
+static int g_sms = 148;
+static double g_clock_ghz = 1.9;
+
+template <typename F>
+static void timeit(const char* name, double ops, F launch) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) launch();
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a));
+    launch();
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  printf("{\"test\": \"%s\", \"ms\": %.4f, \"gops_per_s\": %.2f, \"ops_per_clk_per_sm_at_%.2fGHz\": %.3f}\n", name, best,
+         ops / best * 1e-6, g_clock_ghz, ops / (best * 1e-3) / (g_clock_ghz * 1e9) / g_sms);
+  fflush(stdout);
+}
+
+int main() {
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  g_sms = prop.multiProcessorCount;
+  g_clock_ghz = prop.clockRate * 1e-6;
+  printf("{\"device\": \"%s\", \"sms\": %d, \"clock_ghz\": %.3f, \"l2_mb\": %.1f}\n", prop.name, g_sms, g_clock_ghz,
+         prop.l2CacheSize / 1048576.0);
+  const uint32_t REGION = 448 * 448;          // one image map
+  const uint32_t NREG = 32;
+  float* map; CK(cudaMalloc(&map, sizeof(float) * 4 * (size_t)REGION * NREG));
+  CK(cudaMemset(map, 0, sizeof(float) * 4 * (size_t)REGION * NREG));
+  float* out; CK(cudaMalloc(&out, 16));
+  const int grid = g_sms * 8;
+  const double ops = (double)grid * 256 * ITERS * UNR;
+
+  timeit("gather_global_4B_image_major_784KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION, NREG, out); });
+  timeit("gather_global_8B_image_major_1.5MB", ops, [&] { k_gather_global<float2><<<grid, 256>>>((float2*)map, REGION, NREG, out); });
+  timeit("gather_global_16B_image_major_3MB", ops, [&] { k_gather_global<float4><<<grid, 256>>>((float4*)map, REGION, NREG, out); });
+  timeit("gather_global_4B_whole_25MB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION * NREG, 1, out); });
+  timeit("red_global_f32_image_major_784KB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION, NREG); });
+  timeit("red_global_f32_whole_25MB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION * NREG, 1); });
+
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(k_gather_smem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_gather_smem<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_gather_smem<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_atomic_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid1 = g_sms;   // one 200 KB CTA per SM
+  for (int threads_mult = 1; threads_mult <= 4; threads_mult *= 2) {
+    // 256-thread CTAs, one per SM: vary resident warps by launching several waves is not possible
+    // with 200 KB smem, so report the single-CTA rate (8 warps/SM).
+    (void)threads_mult; break;
+  }
+  const double ops1 = (double)grid1 * 256 * ITERS * UNR;
+  timeit("gather_smem_4B_200KB_8warps", ops1, [&] { k_gather_smem<float><<<grid1, 256, smem>>>(smem / 4, out); });
+  timeit("gather_smem_8B_200KB_8warps", ops1, [&] { k_gather_smem<float2><<<grid1, 256, smem>>>(smem / 8, out); });
+  timeit("gather_smem_16B_200KB_8warps", ops1, [&] { k_gather_smem<float4><<<grid1, 256, smem>>>(smem / 16, out); });
+  timeit("atomic_smem_f32_200KB_8warps", ops1, [&] { k_atomic_smem<<<grid1, 256, smem>>>(smem / 4, out); });
+  // small smem so that 8 CTAs (64 warps) are resident per SM
+  const int smem_small = 24 * 1024;
+  const double ops8 = (double)grid * 256 * ITERS * UNR;
+  timeit("gather_smem_4B_24KB_64warps", ops8, [&] { k_gather_smem<float><<<grid, 256, smem_small>>>(smem_small / 4, out); });
+  timeit("gather_smem_8B_24KB_64warps", ops8, [&] { k_gather_smem<float2><<<grid, 256, smem_small>>>(smem_small / 8, out); });
+  timeit("atomic_smem_f32_24KB_64warps", ops8, [&] { k_atomic_smem<<<grid, 256, smem_small>>>(smem_small / 4, out); });
+
+  // clusters of 8, 100 KB per CTA (two CTAs per SM) and 200 KB (one per SM)
+  {
+    auto launch_cluster = [&](void* fn, int cl, int nblocks, int sm_bytes, uint32_t elems) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = sm_bytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      void* args[] = {&elems, &out};
+      CK(cudaLaunchKernelExC(&cfg, fn, args));
+    };
+    const int smc = 96 * 1024;
+    CK(cudaFuncSetAttribute(k_gather_dsmem<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smc));
+    CK(cudaFuncSetAttribute(k_gather_dsmem<float4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smc));
+    CK(cudaFuncSetAttribute(k_red_dsmem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smc));
+    const int nb = 16 * 8 * 2;   // 32 clusters of 8
+    const double opsc = (double)nb * 256 * ITERS * UNR;
+    timeit("gather_dsmem_4B_cluster8_96KB", opsc, [&] { launch_cluster((void*)k_gather_dsmem<float, 8>, 8, nb, smc, smc / 4); });
+    timeit("gather_dsmem_16B_cluster8_96KB", opsc, [&] { launch_cluster((void*)k_gather_dsmem<float4, 8>, 8, nb, smc, smc / 16); });
+    timeit("red_dsmem_f32_cluster8_96KB", opsc, [&] { launch_cluster((void*)k_red_dsmem<8>, 8, nb, smc, smc / 4); });
+    CK(cudaFuncSetAttribute(k_gather_dsmem<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smc));
+    CK(cudaFuncSetAttribute(k_red_dsmem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smc));
+    const int nb2 = g_sms * 2;
+    const double opsc2 = (double)nb2 * 256 * ITERS * UNR;
+    timeit("gather_dsmem_4B_cluster2_96KB", opsc2, [&] { launch_cluster((void*)k_gather_dsmem<float, 2>, 2, nb2, smc, smc / 4); });
+    timeit("red_dsmem_f32_cluster2_96KB", opsc2, [&] { launch_cluster((void*)k_red_dsmem<2>, 2, nb2, smc, smc / 4); });
+  }
+  timeit("philox4x32_10_calls", (double)grid * 256 * ITERS * UNR, [&] { k_philox<<<grid, 256>>>(out); });
+  return 0;
+}

@@ -283,29 +283,17 @@ def run_b200(args):
         ms_total = float(t.item())
     step.check(dev)
 
-    # ---- dominant kernel alone: fused sample+loss+bwd launch, CUDA events on its stream -----
-    from pldepth_b200._lib import Context, check, c_void_p
-    import ctypes
+    # ---- dominant kernel alone: the library records CUDA events around the list kernel of every
+    # step (pld_ctx_kernel_timing) on its launch stream, over a second pass of the same steps -----
+    from pldepth_b200._lib import Context
     ctx = Context.current(local_rank)
-    lib = ctx.lib
-    kms = []
-    stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    scale = 1.0 / (B * world * R)
-    p = lambda t: c_void_p(t.data_ptr())
-    for i in range(max(5, min(args.steps, 20))):
-        s = sets[i % n_sets]
-        o = s["out"]
-        check(lib.pld_mask_compact(ctx.handle, p(s["mask"]), B, H, W, H, W, p(o["valid_flat"]), p(o["n_valid"]), stream))
-        o["grad"].zero_()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        check(lib.pld_fused_sample_loss_bwd(ctx.handle, p(s["gt"]), p(o["valid_flat"]), p(o["n_valid"]), p(s["pred"]),
-                                            B, HW, HW, K, R, cfg_id, 1000 + i, rank * B, ctypes.c_float(scale),
-                                            p(o["rankings"]), p(o["loss"]), p(o["loss_sum"]), c_void_p(None),
-                                            p(o["grad"]), 1, stream))
-        k1.record()
-        torch.cuda.synchronize()
-        kms.append(k0.elapsed_time(k1))
+    n_k = max(5, min(args.steps, 50))
+    ctx.kernel_timing(n_k)
+    for i in range(n_k):
+        one_step(i)
+    torch.cuda.synchronize()
+    kms = ctx.kernel_times(n_k)
+    ctx.kernel_timing(0)
     kms = sorted(kms)
     k_ms = sum(kms) / len(kms)
     peak, peak_src = peaks()
@@ -370,7 +358,7 @@ def run_b200(args):
                                 "between consecutive steps" % (n_sets, abytes / 1e6),
                        "cuda_graph": bool(graphs)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "lists_small_kernel<K,PHILOX,LOSS> (fused sample+loss+bwd)",
+                         "traffic": traffic, "kernel": "lists_small_kernel<K,PHILOX_TAB,LOSS> (fused sample+order+emit+gather+loss+bwd)",
                          "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
         }

@@ -72,11 +72,22 @@ int pld_ctx_destroy(pld_ctx* ctx);
  * them.  This is how data errors that the reference reports as Python exceptions surface. */
 int pld_ctx_status(pld_ctx* ctx, void* stream, int* status_host);
 
+/* Measurement hook: with slots > 0 the library records a CUDA event pair on the launch stream
+ * around every list-kernel launch (the dominant kernel of each entry point below) into a ring of
+ * `slots` pairs; pld_ctx_kernel_times waits for them, returns the durations in ms and resets the
+ * ring.  slots == 0 switches it off (default). */
+int pld_ctx_kernel_timing(pld_ctx* ctx, int slots);
+int pld_ctx_kernel_times(pld_ctx* ctx, float* ms_host, int capacity, int* count_host);
+
 /* ---- stage 1a: valid-pixel table ----------------------------------------------------------
  * Replaces `mask_points = np.where(mask > 0)` (sampling.py:135), determine_x_y_scales
  * (sampling.py:124-129) and the per-draw `int(rows[sel]*x_scale) * W + int(cols[sel]*y_scale)`
  * (sampling.py:115-119): valid_flat[b][j] = flat image index of the j-th valid mask pixel in
  * row-major order, n_valid[b] = their number.
+ * Identity shortcut: when the mask has the image's resolution and every pixel of image b is
+ * valid, the table would be valid_flat[b][j] == j; the row is then NOT written and n_valid[b] is
+ * stored NEGATED (-Hm*Wm).  Every consumer below takes M = |n_valid[b]| and skips the lookup
+ * for negative counts.
  *   mask f32[B,Hm,Wm] -> valid_flat i32[B,Hm*Wm], n_valid i32[B] */
 int pld_mask_compact(pld_ctx* ctx, const float* mask, int B, int Hm, int Wm, int H, int W,
                      int32_t* valid_flat, int32_t* n_valid, void* stream);
@@ -160,6 +171,23 @@ int pld_fused_sample_loss_bwd(pld_ctx* ctx, const float* gt, const int32_t* vali
                               int image_base, float scale, float* rankings, float* loss,
                               double* loss_sum, float* per_list, float* grad, int accumulate,
                               void* stream);
+
+/* ---- whole step in one call: stages 1a + 1b + 2 + 3 -------------------------------------------
+ * What one training step of the reference does between the data pipeline and the decoder's
+ * backward: np.where(mask) (sampling.py:135) + sample_masked_rankings (sampling.py:131-145, n == R
+ * lists per image) + prepare_fully_fledged_loss_input (depth_utils.py:39-61) + ListMLE loss and
+ * its gradient (nll_loss.py:32-62).  Three launches: mask analysis (+ zeroing of grad), per-image
+ * 8-byte lookup tables in context scratch, fused list kernel.  Outputs are identical to
+ * pld_mask_compact + pld_fused_sample_loss_bwd with the same (seed, offset, image_base).
+ * ranking_size 1..16 only (larger K: use the staged calls).
+ *   mask f32[B,Hm,Wm], gt f32[B,H*W], pred f32[B,H*W]
+ *   -> n_valid i32[B] (nullable; negative = identity table, see pld_mask_compact),
+ *      rankings f32[B,n,K,2] (nullable), loss f32[1], loss_sum f64[1] (nullable),
+ *      per_list f32[B*n] (nullable), grad f32[B,H*W] (nullable = forward only; overwritten) */
+int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
+                   int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
+                   float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
+                   float* per_list, float* grad, void* stream);
 
 #ifdef __cplusplus
 }

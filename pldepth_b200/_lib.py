@@ -28,6 +28,8 @@ SIGNATURES = {
     "pld_ctx_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "pld_ctx_destroy": (c_int, [c_void_p]),
     "pld_ctx_status": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
+    "pld_ctx_kernel_timing": (c_int, [c_void_p, c_int]),
+    "pld_ctx_kernel_times": (c_int, [c_void_p, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_int)]),
     "pld_mask_compact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p]),
     "pld_sample_lists_philox": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -48,6 +50,9 @@ SIGNATURES = {
     "pld_fused_sample_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_u64, c_u64, c_int, c_float, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pld_fused_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_u64, c_u64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
 }
 
 
@@ -122,6 +127,15 @@ class Context(object):
         s = c_int(0)
         check(self.lib.pld_ctx_status(self.handle, c_void_p(stream_ptr), ctypes.byref(s)))
         return s.value
+
+    def kernel_timing(self, slots):
+        check(self.lib.pld_ctx_kernel_timing(self.handle, int(slots)))
+
+    def kernel_times(self, capacity=4096):
+        buf = (c_float * capacity)()
+        n = c_int(0)
+        check(self.lib.pld_ctx_kernel_times(self.handle, buf, capacity, ctypes.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
 
     def raise_on_status(self, stream_ptr):
         s = self.status(stream_ptr)

@@ -31,8 +31,11 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
     }
     return PLD_OK;
   }
-  if (P.K <= 16) return launch_lists_small(P, src, loss, ctx->num_sms, st);
-  return launch_lists_large(P, src, loss, ctx->num_sms, st);
+  ctx->time_begin(st);
+  int rc = (P.K <= 16) ? launch_lists_small(P, src, loss, ctx->num_sms, st)
+                       : launch_lists_large(P, src, loss, ctx->num_sms, st);
+  ctx->time_end(st);
+  return rc;
 }
 
 static void set_rng(ListParams& P, uint64_t seed, uint64_t offset, int image_base) {

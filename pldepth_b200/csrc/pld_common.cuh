@@ -56,8 +56,14 @@ struct pld_ctx {
   int partials_cap;
   void* d_scratch;  // growable scratch (mask chunk counts, MT compaction, radix sort)
   size_t scratch_cap;
+  // optional timing of the dominant (list) kernel: ring of event pairs recorded on the launch stream
+  cudaEvent_t* ev_start;
+  cudaEvent_t* ev_stop;
+  int ev_cap, ev_count;
   int ensure_scratch(size_t bytes);
   int ensure_partials(int n);
+  inline void time_begin(cudaStream_t st) { if (ev_cap > 0 && ev_count < ev_cap) cudaEventRecord(ev_start[ev_count], st); }
+  inline void time_end(cudaStream_t st) { if (ev_cap > 0 && ev_count < ev_cap) { cudaEventRecord(ev_stop[ev_count], st); ++ev_count; } }
 };
 
 namespace pld {

@@ -4,7 +4,7 @@
 
 namespace pld {
 
-enum { SRC_PHILOX = 0, SRC_FED_SEL = 1, SRC_FED_RANK = 2 };
+enum { SRC_PHILOX = 0, SRC_FED_SEL = 1, SRC_FED_RANK = 2, SRC_PHILOX_TAB = 3 };
 
 struct ListParams {
   const float* gt;             // [B, HW]
@@ -13,6 +13,8 @@ struct ListParams {
   const float* pred;           // [B, HW]
   const int32_t* sel_in;       // [B, n, K]   (SRC_FED_SEL)
   const float* rank_in;        // [B, n, K, 2] (SRC_FED_RANK)
+  const float2* table;         // [B, table_stride] (SRC_PHILOX_TAB), see prep_build_kernel
+  size_t table_stride;
   float* rank_out;             // [B, n, K, 2] nullable
   int32_t* sel_out;            // [B, n, K] nullable
   float* per_list;             // [B*n] nullable

@@ -111,11 +111,14 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
   int bad = 0;
 
   uint32_t M = 1, thresh = 0;
+  bool identity = false;
   const int32_t* __restrict__ vflat = nullptr;
   if (SRC != SRC_FED_RANK) {
-    const int m = P.n_valid[b];
-    if (m <= 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
+    const int mraw = P.n_valid[b];
+    const int m = mraw < 0 ? -mraw : mraw;
+    if (m == 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
     else { M = (uint32_t)m; thresh = (0u - M) % M; }
+    identity = mraw < 0;
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
   }
 
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
         for (int i = 0; i < IPL; ++i) {
           const int e = gl * IPL + i;
           if (e < K) {
-            const int q = __ldg(vflat + sel[i]);
+            const int q = identity ? sel[i] : __ldg(vflat + sel[i]);
             const float g = __ldg(gt + q);
             key[i] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)e << 23) | (uint32_t)q;
           } else {

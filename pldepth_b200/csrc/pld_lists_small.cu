@@ -6,7 +6,11 @@ namespace pld {
 
 template <int K, int SRC, bool LOSS>
 __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
+  // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
+  constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
+  __shared__ float2 s_stage[(SRC != SRC_FED_RANK) ? 8 * 32 * STRIDE : 1];
   const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t map_off = (size_t)b * (size_t)P.HW;
   const float* __restrict__ gt = P.gt + map_off;
   const float* __restrict__ pred = P.pred + map_off;
@@ -14,25 +18,31 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
   int bad = 0;
 
   uint32_t M = 1, thresh = 0;
+  bool identity = false;
   const int32_t* __restrict__ vflat = nullptr;
   if (SRC != SRC_FED_RANK) {
-    const int m = P.n_valid[b];
-    if (m <= 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
+    const int mraw = P.n_valid[b];
+    const int m = mraw < 0 ? -mraw : mraw;
+    if (m == 0) { bad |= PLD_ST_EMPTY_MASK; M = 0; }
     else { M = (uint32_t)m; thresh = (0u - M) % M; }
+    identity = mraw < 0;  // full mask at image resolution: valid_flat[j] == j, row not materialised
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
   }
 
   if (M != 0) {
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < P.n; l += gridDim.x * blockDim.x) {
-      const size_t list_id = (size_t)b * (size_t)P.n + (size_t)l;
+    for (int base = blockIdx.x * 256; base < P.n; base += gridDim.x * 256) {
+      const int l = base + threadIdx.x;
+      const bool active = l < P.n;
+      const size_t list_id = (size_t)b * (size_t)P.n + (size_t)(active ? l : P.n - 1);
       int p[K];
       float lab[K];
-      bool valid_all = true;
       uint32_t inval = 0;  // bit k: sorted entry k has an invalid (negative) label
+      float s_tab[K];      // predictions delivered by the (gt, pred) table, sorted order
+      bool have_s = false;
 
       if (SRC == SRC_FED_RANK) {
         const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) + list_id * K;
-        bool sorted = true;
+        bool sorted = true, valid_all = true;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const float2 v = __ldg(rin + k);
@@ -70,10 +80,10 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
       } else {
         uint64_t key[K];
         uint32_t nopay[K];
-        DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16, P.seed_lo,
-                      P.seed_hi};
+        DrawStream ds{(uint32_t)(active ? l : P.n - 1), (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16,
+                      P.seed_lo, P.seed_hi};
         int sel[K];
-        if (SRC == SRC_PHILOX) {
+        if (SRC == SRC_PHILOX || SRC == SRC_PHILOX_TAB) {
 #pragma unroll
           for (int q = 0; q < (K + 3) / 4; ++q) {
             const Philox4 r = ds.block((uint32_t)q);
@@ -93,49 +103,105 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
             sel[k] = s;
           }
         }
-        if (P.sel_out != nullptr && SRC == SRC_PHILOX) {
+        if (P.sel_out != nullptr && (SRC == SRC_PHILOX || SRC == SRC_PHILOX_TAB) && active) {
           int32_t* so = P.sel_out + list_id * K;
 #pragma unroll
           for (int k = 0; k < K; ++k) so[k] = sel[k];
         }
-        int q[K];
+        if (SRC == SRC_PHILOX_TAB) {
+          // per-image lookup table built by prep_build_kernel: one 8-byte gather per draw
+          const float2* __restrict__ tab = P.table + (size_t)b * P.table_stride;
+          float2 t[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) q[k] = __ldg(vflat + sel[k]);
+          for (int k = 0; k < K; ++k) t[k] = __ldg(tab + sel[k]);
+          if (identity) {
+            // full mask: entry j = (gt[j], pred[j]); the prediction rides through the sort as payload
+            uint32_t spay[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const float g = __ldg(gt + q[k]);
-          key[k] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)k << 23) | (uint32_t)q[k];
+            for (int k = 0; k < K; ++k) {
+              key[k] = ((uint64_t)float_to_ordered(t[k].x) << 32) | ((uint32_t)k << 23) | (uint32_t)sel[k];
+              spay[k] = __float_as_uint(t[k].y);
+            }
+            sort_desc_regs<K, true>(key, spay);
+#pragma unroll
+            for (int k = 0; k < K; ++k) s_tab[k] = __uint_as_float(spay[k]);
+            have_s = true;
+          } else {
+            // entry j = (bits of flat index p_j, gt[p_j]) for the j-th valid pixel
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+              key[k] = ((uint64_t)float_to_ordered(t[k].y) << 32) | ((uint32_t)k << 23) | (uint32_t)__float_as_int(t[k].x);
+            sort_desc_regs<K, false>(key, nopay);
+          }
+        } else {
+          int q[K];
+          if (identity) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[k] = sel[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[k] = __ldg(vflat + sel[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const float g = __ldg(gt + q[k]);
+            key[k] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)k << 23) | (uint32_t)q[k];
+          }
+          sort_desc_regs<K, false>(key, nopay);
         }
-        sort_desc_regs<K, false>(key, nopay);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           p[k] = (int)((uint32_t)key[k] & 0x7FFFFFu);
           lab[k] = ordered_to_float((uint32_t)(key[k] >> 32));
         }
         if (P.rank_out != nullptr) {
-          float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K;
+          float2* st = s_stage + wid * (32 * STRIDE);
 #pragma unroll
-          for (int k = 0; k < K; ++k) ro[k] = make_float2((float)p[k], lab[k]);
+          for (int k = 0; k < K; ++k) st[lane * STRIDE + k] = make_float2((float)p[k], lab[k]);
+          __syncwarp();
+          const int warp_first = base + wid * 32;              // first list of this warp
+          int cnt = P.n - warp_first;                          // active lists in this warp
+          cnt = cnt > 32 ? 32 : cnt;
+          if (cnt > 0) {
+            float2* ro = reinterpret_cast<float2*>(P.rank_out) + ((size_t)b * (size_t)P.n + (size_t)warp_first) * K;
+            const int total = cnt * K;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const int e = i * 32 + lane;
+              if (e < total) {
+                const int li = e / K, kk = e - li * K;
+                ro[e] = st[li * STRIDE + kk];
+              }
+            }
+          }
+          __syncwarp();
         }
       }
 
       if (LOSS) {
         float s[K], g[K];
+        if (have_s) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) s[k] = __ldg(pred + p[k]);
+          for (int k = 0; k < K; ++k) s[k] = s_tab[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) s[k] = __ldg(pred + p[k]);
+        }
         if (inval) {
 #pragma unroll
           for (int k = 0; k < K; ++k)
             if ((inval >> k) & 1u) s[k] = PLD_LOG_EPS;
         }
         const float nll = listmle_regs<K>(s, g);
-        local += nll;
-        if (P.per_list != nullptr) P.per_list[list_id] = nll;
-        if (P.grad != nullptr) {
-          float* gr = P.grad + map_off;
+        if (active) {
+          local += nll;
+          if (P.per_list != nullptr) P.per_list[list_id] = nll;
+          if (P.grad != nullptr) {
+            float* gr = P.grad + map_off;
 #pragma unroll
-          for (int k = 0; k < K; ++k)
-            if (!((inval >> k) & 1u)) atomicAdd(gr + p[k], g[k] * P.scale);
+            for (int k = 0; k < K; ++k)
+              if (!((inval >> k) & 1u)) atomicAdd(gr + p[k], g[k] * P.scale);
+          }
         }
       }
     }
@@ -172,6 +238,7 @@ int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cud
   if (src == SRC_PHILOX) return loss ? launch_small_k<SRC_PHILOX, true>(P, grid, st) : launch_small_k<SRC_PHILOX, false>(P, grid, st);
   if (src == SRC_FED_SEL) return loss ? launch_small_k<SRC_FED_SEL, true>(P, grid, st) : launch_small_k<SRC_FED_SEL, false>(P, grid, st);
   if (src == SRC_FED_RANK) return launch_small_k<SRC_FED_RANK, true>(P, grid, st);
+  if (src == SRC_PHILOX_TAB) return launch_small_k<SRC_PHILOX_TAB, true>(P, grid, st);
   set_error("lists_small: bad source %d", src);
   return PLD_EINVAL;
 }

@@ -126,6 +126,23 @@ __global__ void __launch_bounds__(MC_THREADS) mask_scatter_kernel(
     s_prefix = t;
   }
   __syncthreads();
+  if (identity) {
+    // full mask at image resolution: the table would be valid_flat[j] == j; it is not written
+    // and the count is stored negated so consumers skip the lookup (include/pldepth_b200.h)
+    int tot = 0;
+    for (int i = threadIdx.x; i < nchunks; i += MC_THREADS) tot += counts[b * nchunks + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __shared__ int s_tot[MC_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    tot = 0;
+    for (int i = 0; i < MC_THREADS / 32; ++i) tot += s_tot[i];
+    if (tot == Nm) {
+      if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
+      return;
+    }
+  }
   const int base = chunk * MC_CHUNK + threadIdx.x * MC_ITEMS;
   const uint32_t f = (base < Nm) ? mask_flags16(m, base, Nm) : 0u;
   const int c = __popc(f);
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(MTC_THREADS) mt_count_kernel(const uint32_t* _
                                                                const long long* __restrict__ cons,
                                                                const int32_t* __restrict__ n_valid,
                                                                int b, int* __restrict__ counts) {
-  const uint32_t M = (uint32_t)n_valid[b];
+  const uint32_t M = (uint32_t)abs(n_valid[b]);
   int c = 0;
   if ((int)M > 1) {
     const uint32_t msk = np_mask(M);
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(1024) mt_scan_kernel(int* counts, int nblk, in
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const int M = n_valid[b];
+    const int M = abs(n_valid[b]);
     if (M > 1 && s_carry < need) atomicOr(status, PLD_ST_MT_EXHAUSTED);
     if (M <= 0) atomicOr(status, PLD_ST_EMPTY_MASK);
     cons[b + 1] = n_raw;  // "exhausted" marker; the scatter pass overwrites it on success
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(MTC_THREADS) mt_scatter_kernel(
     const uint32_t* __restrict__ raw, long long n_raw, long long* __restrict__ cons,
     const int32_t* __restrict__ n_valid, int b, const int* __restrict__ offsets, int need,
     int32_t* __restrict__ sel) {
-  const uint32_t M = (uint32_t)n_valid[b];
+  const uint32_t M = (uint32_t)abs(n_valid[b]);
   const long long start = cons[b];
   if ((int)M <= 1) {  // randint(1) consumes no word and returns 0
     for (int i = blockIdx.x * MTC_THREADS + threadIdx.x; i < need; i += gridDim.x * MTC_THREADS) sel[i] = 0;
@@ -597,7 +614,35 @@ int pld_ctx_destroy(pld_ctx* ctx) {
   cudaFree(ctx->d_ticket);
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_scratch);
+  pld_ctx_kernel_timing(ctx, 0);
   delete ctx;
+  return PLD_OK;
+}
+
+int pld_ctx_kernel_timing(pld_ctx* ctx, int slots) {
+  PLD_REQUIRE(ctx && slots >= 0 && slots <= 4096, "bad argument");
+  for (int i = 0; i < ctx->ev_cap; ++i) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
+  delete[] ctx->ev_start; delete[] ctx->ev_stop;
+  ctx->ev_start = ctx->ev_stop = nullptr;
+  ctx->ev_cap = ctx->ev_count = 0;
+  if (slots > 0) {
+    ctx->ev_start = new cudaEvent_t[slots];
+    ctx->ev_stop = new cudaEvent_t[slots];
+    for (int i = 0; i < slots; ++i) { PLD_CUDA(cudaEventCreate(&ctx->ev_start[i])); PLD_CUDA(cudaEventCreate(&ctx->ev_stop[i])); }
+    ctx->ev_cap = slots;
+  }
+  return PLD_OK;
+}
+
+int pld_ctx_kernel_times(pld_ctx* ctx, float* ms_host, int capacity, int* count_host) {
+  PLD_REQUIRE(ctx && ms_host && count_host && capacity >= 0, "bad argument");
+  int n = ctx->ev_count < capacity ? ctx->ev_count : capacity;
+  for (int i = 0; i < n; ++i) {
+    PLD_CUDA(cudaEventSynchronize(ctx->ev_stop[i]));
+    PLD_CUDA(cudaEventElapsedTime(&ms_host[i], ctx->ev_start[i], ctx->ev_stop[i]));
+  }
+  *count_host = n;
+  ctx->ev_count = 0;
   return PLD_OK;
 }
 

@@ -41,7 +41,9 @@ def _ctx(t):
 
 
 def mask_compact(mask, H, W):
-    """mask f32[B,Hm,Wm] -> (valid_flat i32[B,Hm*Wm], n_valid i32[B]).  sampling.py:124-135."""
+    """mask f32[B,Hm,Wm] -> (valid_flat i32[B,Hm*Wm], n_valid i32[B]).  sampling.py:124-135.
+    A negative n_valid[b] marks the identity table of a fully valid image-resolution mask (row
+    not written; M = -n_valid[b]) -- see include/pldepth_b200.h."""
     mask = as_cuda(mask, torch.float32, "mask")
     if mask.dim() == 2:
         mask = mask.unsqueeze(0)
@@ -222,6 +224,34 @@ def fused_sample_loss_bwd(gt, valid_flat, n_valid, pred, K, n, seed, offset=0, i
                                                 _p(loss_sum), _p(per_list), _p(grad), 1 if accumulate else 0,
                                                 _stream(dev)))
     return loss, loss_sum, grad, rankings, per_list
+
+
+def fused_step(mask, gt, pred, K, n, seed, offset=0, image_base=0, scale=None, want_rankings=True, want_grad=True,
+               want_per_list=False):
+    """pld_fused_step: mask f32[B,Hm,Wm], gt f32[B,H,W], pred f32[B,H,W(,1)] -> (loss, loss_sum, grad,
+    rankings, per_list, n_valid).  ranking_size <= 16."""
+    mask = as_cuda(mask, torch.float32, "mask")
+    gt3 = as_cuda(gt, torch.float32, "gt")
+    if gt3.dim() == 4:
+        gt3 = gt3[..., 0].contiguous()
+    pred = as_cuda(pred, torch.float32, "pred")
+    B, H, W = gt3.shape
+    Hm, Wm = mask.shape[1], mask.shape[2]
+    if scale is None:
+        scale = 1.0 / float(B * n)
+    ctx = _ctx(gt3)
+    dev = gt3.device
+    with torch.cuda.device(dev):
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        loss_sum = torch.empty(1, dtype=torch.float64, device=dev)
+        n_valid = torch.empty(B, dtype=torch.int32, device=dev)
+        rankings = torch.empty((B, n, K, 2), dtype=torch.float32, device=dev) if want_rankings else None
+        grad = torch.empty_like(pred) if want_grad else None
+        per_list = torch.empty(B * n, dtype=torch.float32, device=dev) if want_per_list else None
+        check(ctx.lib.pld_fused_step(ctx.handle, _p(mask), _p(gt3), _p(pred), B, Hm, Wm, H, W, int(K), int(n), int(seed),
+                                     int(offset), int(image_base), float(scale), _p(n_valid), _p(rankings), _p(loss),
+                                     _p(loss_sum), _p(per_list), _p(grad), _stream(dev)))
+    return loss, loss_sum, grad, rankings, per_list, n_valid
 
 
 def check_status(device=None):

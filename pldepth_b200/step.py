@@ -4,7 +4,8 @@ ListMLE forward + backward, for a batch of images resident on one GPU.
 This is what replaces, per training step, the reference's tf.data sampler map
 (hourglass_provider.py:55-62), ``prepare_fully_fledged_loss_input`` (depth_utils.py:39-61) and the
 TF-Ranking ListMLE loss + its autodiff (nll_loss.py:32-62).  Output buffers are preallocated and
-reused, so a step is three kernel launches and one memset on the current stream, no host sync.
+reused, so a step is three kernel launches on the current stream (ranking_size <= 16; two launches +
+memset + list kernel above that), no host sync.
 """
 import ctypes
 
@@ -55,6 +56,14 @@ class FusedPLStep(object):
         gb = self.global_batch if self.global_batch else B
         scale = 1.0 / (float(gb) * float(self.R))
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+        if self.K <= 16:
+            # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
+            check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
+                                     self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
+                                     p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),
+                                     p(buf["grad"]), stream))
+            self.step_index += 1
+            return buf
         check(lib.pld_mask_compact(ctx.handle, p(mask), B, Hm, Wm, H, W, p(buf["valid_flat"]), p(buf["n_valid"]),
                                    stream))
         check(lib.pld_fused_sample_loss_bwd(ctx.handle, p(gt), p(buf["valid_flat"]), p(buf["n_valid"]), p(pred), B,

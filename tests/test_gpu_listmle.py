@@ -144,6 +144,39 @@ def test_fused_equals_sample_then_loss(cuda_device, K, n):
     assert g3 is None and r3 is None and l3.item() == loss.item()
 
 
+@pytest.mark.parametrize("K,n", [(1, 50), (2, 400), (5, 1500), (8, 700), (16, 300)])
+@pytest.mark.parametrize("geometry", ["full", "holes", "scaled"])
+def test_one_call_step_equals_staged_calls(cuda_device, K, n, geometry):
+    """pld_fused_step (lookup tables + fused kernel) == pld_mask_compact + pld_fused_sample_loss_bwd:
+    rankings and per-list NLL bit for bit, gradient within tolerance, for full / holed / down-scaled masks."""
+    from pldepth_b200 import ops
+    from tests.test_gpu_sampler import make_maps
+    B, H, W = 3, 40, 48
+    Hm, Wm = (20, 16) if geometry == "scaled" else (H, W)
+    gt, mask = make_maps(H, W, Hm, Wm, 7 * K, B, hole=(geometry != "full"))
+    if geometry == "holes":
+        mask[1] = 1.0                           # mix of full and holed images in one batch
+    pred = np.random.RandomState(K).randn(B, H, W, 1).astype(np.float32)
+    gt_d, pred_d, mask_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, pred, mask))
+    loss, loss_sum, grad, rank, pl, nv = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=5, offset=9, image_base=2,
+                                                        want_per_list=True)
+    vf, nv2 = ops.mask_compact(mask_d, H, W)
+    assert torch.equal(nv, nv2)
+    loss2, ls2, grad2, rank2, pl2 = ops.fused_sample_loss_bwd(gt_d, vf, nv2, pred_d, K, n, seed=5, offset=9,
+                                                              image_base=2, want_per_list=True)
+    ops.check_status(cuda_device)
+    assert torch.equal(rank, rank2)
+    assert torch.equal(pl, pl2)
+    assert loss.item() == loss2.item() and loss_sum.item() == ls2.item()
+    assert_close(grad.cpu().numpy(), grad2.cpu().numpy(), "one-call vs staged gradient")
+    want_loss, want_grad, _ = lo.hourglass_nll(rank.cpu().numpy(), pred, B, K)
+    assert_close(loss.item(), want_loss, "loss")
+    assert_close(grad.cpu().numpy(), want_grad, "gradient")
+    for b in range(B):                          # never a masked-out pixel
+        valid = set(so.valid_flat_indices(mask[b], (H, W)).tolist())
+        assert set(rank[b, :, :, 0].long().flatten().tolist()) <= valid
+
+
 def test_loss_is_deterministic(cuda_device):
     from pldepth_b200 import ops
     y_true, pred = make_problem(4, 64, 64, 5, 5000, 3)

@@ -46,6 +46,55 @@ __global__ void __launch_bounds__(256) k_red_global(float* __restrict__ map, uin
   }
 }
 
+// texture path / mixed LSU+TEX / scattered stores
+__global__ void __launch_bounds__(256) k_gather_tex(cudaTextureObject_t tex, uint32_t region_elems, uint32_t n_regions,
+                                                    float* out) {
+  const uint32_t off = (blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) acc += tex1Dfetch<float>(tex, (int)(off + __umulhi(xs32(s), region_elems)));
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+__global__ void __launch_bounds__(256) k_gather_mixed(cudaTextureObject_t tex, const float* __restrict__ table,
+                                                      uint32_t region_elems, uint32_t n_regions, float* out) {
+  const uint32_t off = (blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; u += 2) {
+      acc += tex1Dfetch<float>(tex, (int)(off + __umulhi(xs32(s), region_elems)));
+      acc += __ldg(table + off + __umulhi(xs32(s), region_elems));
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+__global__ void __launch_bounds__(256) k_scatter_store8(float2* __restrict__ map, uint32_t region_elems,
+                                                        uint32_t n_regions) {
+  float2* base = map + (size_t)(blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 777u;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) base[__umulhi(xs32(s), region_elems)] = make_float2((float)it, (float)u);
+  }
+}
+// gather + red on the same address (pred gather then grad atomic on a paired map)
+__global__ void __launch_bounds__(256) k_gather_then_red(const float* __restrict__ table, float* __restrict__ map,
+                                                         uint32_t region_elems, uint32_t n_regions) {
+  const size_t off = (size_t)(blockIdx.x % n_regions) * region_elems;
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 99u;
+  for (int it = 0; it < ITERS; ++it) {
+    uint32_t idx[UNR]; float v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) { idx[u] = __umulhi(xs32(s), region_elems); v[u] = __ldg(table + off + idx[u]); }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) atomicAdd(map + off + idx[u], v[u] + 1.0f);
+  }
+}
+
 // ---- shared memory --------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_smem(uint32_t elems, float* out) {
@@ -195,6 +244,16 @@ int main() {
   timeit("red_global_f32_image_major_784KB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION, NREG); });
   timeit("red_global_f32_whole_25MB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION * NREG, 1); });
 
+  {
+    cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = map;
+    rd.res.linear.desc = cudaCreateChannelDesc<float>(); rd.res.linear.sizeInBytes = sizeof(float) * (size_t)REGION * NREG;
+    cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex; CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    timeit("gather_tex1Dfetch_4B_image_major", ops, [&] { k_gather_tex<<<grid, 256>>>(tex, REGION, NREG, out); });
+    timeit("gather_mixed_tex+ldg_4B_image_major", ops, [&] { k_gather_mixed<<<grid, 256>>>(tex, map, REGION, NREG, out); });
+    timeit("scatter_store_8B_image_major", ops, [&] { k_scatter_store8<<<grid, 256>>>((float2*)map, REGION, NREG); });
+    timeit("gather4B_then_red_pairs(ops=pairs)", ops, [&] { k_gather_then_red<<<grid, 256>>>(map, map + (size_t)REGION * NREG, REGION, NREG); });
+  }
   const int smem = 200 * 1024;
   CK(cudaFuncSetAttribute(k_gather_smem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_gather_smem<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

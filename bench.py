@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for cpu_baseline")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--hole", type=float, default=0.0, help="fraction of each mask zeroed (default: all-ones mask)")
     return ap.parse_args()
 
 
@@ -209,7 +210,7 @@ def run_b200(args):
     # synthetic maps: a few distinct rank-transformed fields, rolled to make B distinct images
     base_maps = [synth.depth_map(H, W, 1000 * cfg_id + 17 * rank + i) for i in range(min(B, 4))]
     gt_h = np.stack([np.roll(base_maps[b % len(base_maps)], 31 * b, axis=1) for b in range(B)])
-    mask_h = np.ones((B, H, W), np.float32)
+    mask_h = np.stack([synth.valid_mask(H, W, 3000 * cfg_id + b, args.hole) for b in range(B)])
     rs = np.random.RandomState(2000 * cfg_id + rank)
     pred_h = rs.standard_normal((B, H, W, 1)).astype(np.float32)
 
@@ -351,8 +352,10 @@ def run_b200(args):
             "metric": METRIC, "value": L * world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s per GPU: B=%d images %dx%d, ranking_size K=%d, R=%d lists/image, all-ones "
-                                   "mask, core sampler (factor 1.0), rankings emitted" % (args.workload, B, H, W, K, R),
+            "config": {"workload": "%s per GPU: B=%d images %dx%d, ranking_size K=%d, R=%d lists/image, %s "
+                                   "mask, core sampler (factor 1.0), rankings emitted" % (
+                                       args.workload, B, H, W, K, R,
+                                       "all-ones" if args.hole == 0 else "%.0f%%-hole" % (100 * args.hole)),
                        "lists_per_step": L * world, "sharding": "per image, %d GPU(s)" % world,
                        "cache": "rotating %d input/output buffer sets of %.0f MB each (> 126 MB L2), no reuse "
                                 "between consecutive steps" % (n_sets, abytes / 1e6),

@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpldepth_b200.so")
+LIB_PATH = os.environ.get("PLDEPTH_B200_LIB") or os.path.join(_HERE, "libpldepth_b200.so")
 
 PLD_MAX_RANKING_SIZE = 512
 PLD_MAX_PIXELS = 1 << 23

@@ -32,6 +32,15 @@ struct ListParams {
 
 #define PLD_LOG_EPS (-23.025850929940457f) /* float32(log(1e-10)), TF-Ranking _EPSILON */
 
+// fire-and-forget float add into the dense gradient map (RED, no return value)
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+#ifdef PLD_USE_ATOMG
+  atomicAdd(addr, v);
+#else
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+#endif
+}
+
 // compare-exchange, descending (a >= b afterwards)
 __device__ __forceinline__ void ce_desc(uint64_t& a, uint64_t& b) {
   const bool sw = a < b;

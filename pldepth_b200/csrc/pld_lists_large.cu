@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
               if (gl * IPL + i < K && !((inval >> i) & 1u))
-                atomicAdd(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
+                red_add_f32(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
           }
         }
       }

@@ -4,8 +4,28 @@
 
 namespace pld {
 
+// K Philox draws of list l of image (image_base + b), mapped to [0, M)
+template <int K>
+__device__ __forceinline__ void draw_philox(const ListParams& P, int b, int l, uint32_t M, uint32_t thresh,
+                                            int (&sel)[K]) {
+  const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16, P.seed_lo, P.seed_hi};
+#pragma unroll
+  for (int q = 0; q < (K + 3) / 4; ++q) {
+    const Philox4 r = ds.block((uint32_t)q);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = q * 4 + j;
+      if (k < K) sel[k] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)k);
+    }
+  }
+}
+
+#ifndef PLD_SMALL_MINBLOCKS
+#define PLD_SMALL_MINBLOCKS 1
+#endif
 template <int K, int SRC, bool LOSS>
-__global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
+__global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
   __shared__ float2 s_stage[(SRC != SRC_FED_RANK) ? 8 * 32 * STRIDE : 1];
@@ -27,6 +47,21 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
     else { M = (uint32_t)m; thresh = (0u - M) % M; }
     identity = mraw < 0;  // full mask at image resolution: valid_flat[j] == j, row not materialised
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
+  }
+
+  // software pipeline of the table path: the draws and table gathers of the NEXT list are issued
+  // before the current list is ordered / scored, so their latency hides behind that work
+  int pre_sel[K];
+  float2 pre_t[K];
+  const float2* __restrict__ tab = nullptr;
+  if (SRC == SRC_PHILOX_TAB && M != 0) {
+    tab = P.table + (size_t)b * P.table_stride;
+    const int l0 = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x * 256 < P.n) {
+      draw_philox<K>(P, b, l0 < P.n ? l0 : P.n - 1, M, thresh, pre_sel);
+#pragma unroll
+      for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
+    }
   }
 
   if (M != 0) {
@@ -80,20 +115,20 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
       } else {
         uint64_t key[K];
         uint32_t nopay[K];
-        DrawStream ds{(uint32_t)(active ? l : P.n - 1), (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16,
-                      P.seed_lo, P.seed_hi};
         int sel[K];
-        if (SRC == SRC_PHILOX || SRC == SRC_PHILOX_TAB) {
+        float2 t[K];
+        if (SRC == SRC_PHILOX_TAB) {
 #pragma unroll
-          for (int q = 0; q < (K + 3) / 4; ++q) {
-            const Philox4 r = ds.block((uint32_t)q);
-            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+          for (int k = 0; k < K; ++k) { sel[k] = pre_sel[k]; t[k] = pre_t[k]; }
+          const int nbase = base + gridDim.x * 256;
+          if (nbase < P.n) {
+            const int ln = nbase + threadIdx.x;
+            draw_philox<K>(P, b, ln < P.n ? ln : P.n - 1, M, thresh, pre_sel);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int k = q * 4 + j;
-              if (k < K) sel[k] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)k);
-            }
+            for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
           }
+        } else if (SRC == SRC_PHILOX) {
+          draw_philox<K>(P, b, active ? l : P.n - 1, M, thresh, sel);
         } else {
           const int32_t* __restrict__ sin = P.sel_in + list_id * K;
 #pragma unroll
@@ -110,10 +145,6 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
         }
         if (SRC == SRC_PHILOX_TAB) {
           // per-image lookup table built by prep_build_kernel: one 8-byte gather per draw
-          const float2* __restrict__ tab = P.table + (size_t)b * P.table_stride;
-          float2 t[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) t[k] = __ldg(tab + sel[k]);
           if (identity) {
             // full mask: entry j = (gt[j], pred[j]); the prediction rides through the sort as payload
             uint32_t spay[K];
@@ -200,7 +231,7 @@ __global__ void __launch_bounds__(256) lists_small_kernel(const ListParams P) {
             float* gr = P.grad + map_off;
 #pragma unroll
             for (int k = 0; k < K; ++k)
-              if (!((inval >> k) & 1u)) atomicAdd(gr + p[k], g[k] * P.scale);
+              if (!((inval >> k) & 1u)) red_add_f32(gr + p[k], g[k] * P.scale);
           }
         }
       }

@@ -125,6 +125,13 @@ __device__ __forceinline__ uint32_t lemire_bounded(uint32_t word, uint32_t M, ui
   return (uint32_t)(m >> 32);
 }
 
+// branch-free first attempt: returns the mapped value and ORs "needs the redraw path" into rej
+__device__ __forceinline__ uint32_t lemire_try(uint32_t word, uint32_t M, uint32_t thresh, bool& rej) {
+  const uint64_t m = (uint64_t)word * (uint64_t)M;
+  rej = rej || ((uint32_t)m < thresh);
+  return (uint32_t)(m >> 32);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,8 +5,11 @@
 
 namespace pld {
 
+// Bitonic network over LPL*IPL slots (slot e = lane*IPL + i), descending, keys as (hi, lo)
+// 32-bit halves.  All keys are distinct (pads: all zero, interchangeable), so "take the partner"
+// is a single predicate and the whole network is branch-free SEL code.
 template <int LPL, int IPL, bool PAYLOAD>
-__device__ __forceinline__ void bitonic_desc(uint64_t (&key)[IPL], uint32_t (&pay)[IPL], int gl) {
+__device__ __forceinline__ void bitonic_desc(uint32_t (&khi)[IPL], uint32_t (&klo)[IPL], uint32_t (&pay)[IPL], int gl) {
   constexpr int N = LPL * IPL;
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
@@ -19,23 +22,29 @@ __device__ __forceinline__ void bitonic_desc(uint64_t (&key)[IPL], uint32_t (&pa
         const bool keep_max = (up == lower);
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[i], lm);
-          const bool take = keep_max ? (other > key[i]) : (other < key[i]);
+          const uint32_t ohi = __shfl_xor_sync(0xffffffffu, khi[i], lm);
+          const uint32_t olo = __shfl_xor_sync(0xffffffffu, klo[i], lm);
+          const bool gt = (((uint64_t)ohi << 32) | olo) > (((uint64_t)khi[i] << 32) | klo[i]);
+          const bool take = (gt == keep_max);
           if (PAYLOAD) {
             const uint32_t op = __shfl_xor_sync(0xffffffffu, pay[i], lm);
             pay[i] = take ? op : pay[i];
           }
-          key[i] = take ? other : key[i];
+          khi[i] = take ? ohi : khi[i];
+          klo[i] = take ? olo : klo[i];
         }
       } else {
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
           if ((i & j) == 0) {
             const bool up = (((gl * IPL + i) & k) == 0);
-            uint64_t a = key[i], b = key[i | j];
-            const bool sw = up ? (a < b) : (a > b);
-            key[i] = sw ? b : a;
-            key[i | j] = sw ? a : b;
+            const uint32_t ah = khi[i], al = klo[i], bh = khi[i | j], bl = klo[i | j];
+            const bool lt = (((uint64_t)ah << 32) | al) < (((uint64_t)bh << 32) | bl);
+            const bool sw = (lt == up);
+            khi[i] = sw ? bh : ah;
+            klo[i] = sw ? bl : al;
+            khi[i | j] = sw ? ah : bh;
+            klo[i | j] = sw ? al : bl;
             if (PAYLOAD) {
               const uint32_t pa = pay[i], pb = pay[i | j];
               pay[i] = sw ? pb : pa;
@@ -96,14 +105,19 @@ __device__ __forceinline__ float group_excl_prefix(float v, int gl) {
   return x;
 }
 
+#ifndef PLD_LARGE_MINBLOCKS
+#define PLD_LARGE_MINBLOCKS 4
+#endif
 template <int LPL, int IPL, int SRC, bool LOSS>
-__global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
+__global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(const ListParams P) {
   constexpr int GPW = 32 / LPL;    // groups per warp
   constexpr int GPB = 256 / LPL;   // groups per block
   const int K = P.K;
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (LPL - 1);
+  // bit i set <=> slot gl*IPL + i holds a real entry (slot index < K)
+  const uint32_t emask = (K - gl * IPL >= IPL) ? ((1u << IPL) - 1u) : ((K - gl * IPL > 0) ? ((1u << (K - gl * IPL)) - 1u) : 0u);
   const size_t map_off = (size_t)b * (size_t)P.HW;
   const float* __restrict__ gt = P.gt + map_off;
   const float* __restrict__ pred = P.pred + map_off;
@@ -164,21 +178,17 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
             if (gl * IPL + i < K) mn = fminf(mn, lab[i] >= 0.f ? lab[i] : 0.f);
           mn = group_min<LPL>(mn);
           const float inv_key = mn - 1e-6f;
-          uint64_t key[IPL];
-          uint32_t pay[IPL];
+          uint32_t khi[IPL], klo[IPL], pay[IPL];
 #pragma unroll
           for (int i = 0; i < IPL; ++i) {
             const int e = gl * IPL + i;
-            if (e < K) {
-              const bool v = lab[i] >= 0.f;
-              key[i] = ((uint64_t)float_to_ordered(v ? lab[i] : inv_key) << 32) | (uint32_t)(0xFFFF - e);
-              pay[i] = (uint32_t)p[i] | (v ? 0u : 0x80000000u);
-            } else {
-              key[i] = 0ull;
-              pay[i] = 0u;
-            }
+            const bool on = e < K;
+            const bool v = lab[i] >= 0.f;
+            khi[i] = on ? float_to_ordered(v ? lab[i] : inv_key) : 0u;
+            klo[i] = on ? (uint32_t)(0xFFFF - e) : 0u;
+            pay[i] = on ? ((uint32_t)p[i] | (v ? 0u : 0x80000000u)) : 0u;
           }
-          bitonic_desc<LPL, IPL, true>(key, pay, gl);
+          bitonic_desc<LPL, IPL, true>(khi, klo, pay, gl);
 #pragma unroll
           for (int i = 0; i < IPL; ++i) {
             p[i] = (int)(pay[i] & 0x7FFFFFFFu);
@@ -186,65 +196,83 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
           }
         }
       } else {
-        uint64_t key[IPL];
-        uint32_t nopay[IPL];
+        uint32_t khi[IPL], klo[IPL], nopay[IPL];
         const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16,
                             P.seed_lo, P.seed_hi};
         int sel[IPL];
 #pragma unroll
         for (int i = 0; i < IPL; ++i) sel[i] = 0;
         if (SRC == SRC_PHILOX) {
+          bool rej = false;
 #pragma unroll
           for (int q = 0; q < IPL / 4; ++q) {
             const int e0 = gl * IPL + q * 4;
             if (e0 < K) {
               const Philox4 r = ds.block((uint32_t)(e0 >> 2));
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+              sel[q * 4 + 0] = (int)lemire_try(r.x, M, thresh, rej);
+              sel[q * 4 + 1] = (int)lemire_try(r.y, M, thresh, rej);
+              sel[q * 4 + 2] = (int)lemire_try(r.z, M, thresh, rej);
+              sel[q * 4 + 3] = (int)lemire_try(r.w, M, thresh, rej);
+            }
+          }
+          if (rej) {  // rare (P < K * M / 2^32): redo this lane's draws with the redraw stream
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (e0 + j < K) sel[q * 4 + j] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)(e0 + j));
+            for (int q = 0; q < IPL / 4; ++q) {
+              const int e0 = gl * IPL + q * 4;
+              if (e0 < K) {
+                const Philox4 r = ds.block((uint32_t)(e0 >> 2));
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sel[q * 4 + j] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)(e0 + j));
+              }
             }
           }
           if (P.sel_out != nullptr && active) {
             int32_t* so = P.sel_out + list_id * K;
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
-              if (gl * IPL + i < K) so[gl * IPL + i] = sel[i];
+              if ((emask >> i) & 1u) so[gl * IPL + i] = sel[i];
           }
         } else {
           const int32_t* __restrict__ sin = P.sel_in + list_id * K;
 #pragma unroll
           for (int i = 0; i < IPL; ++i) {
             const int e = gl * IPL + i;
-            if (e < K) {
-              int s = __ldg(sin + e);
-              if (s < 0 || (uint32_t)s >= M) { bad |= PLD_ST_BAD_INDEX; s = 0; }
-              sel[i] = s;
-            }
+            int s = __ldg(sin + (e < K ? e : 0));
+            if (s < 0 || (uint32_t)s >= M) { bad |= PLD_ST_BAD_INDEX; s = 0; }
+            sel[i] = s;
           }
         }
+        // pad slots read entry 0 (always valid) and get the smallest key, so they sort last
+        int qv[IPL];
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) qv[i] = identity ? sel[i] : __ldg(vflat + sel[i]);
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          const int e = gl * IPL + i;
-          if (e < K) {
-            const int q = identity ? sel[i] : __ldg(vflat + sel[i]);
-            const float g = __ldg(gt + q);
-            key[i] = ((uint64_t)float_to_ordered(g) << 32) | ((uint32_t)e << 23) | (uint32_t)q;
-          } else {
-            key[i] = 0ull;
-          }
+          const float g = __ldg(gt + qv[i]);
+          const bool on = (emask >> i) & 1u;
+          khi[i] = on ? float_to_ordered(g) : 0u;
+          klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)qv[i]) : 0u;
         }
-        bitonic_desc<LPL, IPL, false>(key, nopay, gl);
+        bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          p[i] = (int)((uint32_t)key[i] & 0x7FFFFFu);
-          lab[i] = ordered_to_float((uint32_t)(key[i] >> 32));
+          p[i] = (int)(klo[i] & 0x7FFFFFu);
+          lab[i] = ordered_to_float(khi[i]);
         }
         if (P.rank_out != nullptr && active) {
-          float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K;
+          float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K + gl * IPL;
+          if ((K & 1) == 0) {  // 16-byte stores: list rows are 16-byte aligned when K is even
 #pragma unroll
-          for (int i = 0; i < IPL; ++i)
-            if (gl * IPL + i < K) ro[gl * IPL + i] = make_float2((float)p[i], lab[i]);
+            for (int i = 0; i < IPL; i += 2)
+              if ((emask >> i) & 1u)
+                *reinterpret_cast<float4*>(ro + i) = make_float4((float)p[i], lab[i], (float)p[i + 1], lab[i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < IPL; ++i)
+              if ((emask >> i) & 1u) ro[i] = make_float2((float)p[i], lab[i]);
+          }
         }
       }
 
@@ -253,18 +281,15 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
         float m = -3.402823466e38f;
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          const int e = gl * IPL + i;
-          s[i] = 0.f;
-          if (e < K) {
-            s[i] = ((inval >> i) & 1u) ? PLD_LOG_EPS : __ldg(pred + p[i]);
-            m = fmaxf(m, s[i]);
-          }
+          const float sv = __ldg(pred + p[i]);  // pad slots hold p == 0: a valid address
+          s[i] = ((emask >> i) & 1u) ? (((inval >> i) & 1u) ? PLD_LOG_EPS : sv) : -3.402823466e38f;
+          m = fmaxf(m, s[i]);
         }
         m = group_max<LPL>(m);
         float run = 0.f;
 #pragma unroll
         for (int i = IPL - 1; i >= 0; --i) {
-          ex[i] = (gl * IPL + i < K) ? expf(s[i] - m) : 0.f;
+          ex[i] = __expf(s[i] - m);  // ex2.approx path; pads: exp(-3.4e38) == 0
           run += ex[i];
           S[i] = run;
         }
@@ -273,13 +298,12 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
         float cl[IPL];
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          cl[i] = 0.f;
-          if (gl * IPL + i < K) {
-            S[i] += carry;
-            nll += logf(S[i]) - (s[i] - m);
-            c += 1.0f / S[i];
-            cl[i] = c;
-          }
+          const bool on = (emask >> i) & 1u;
+          S[i] += carry;
+          const float term = __logf(S[i]) - (s[i] - m);
+          nll += on ? term : 0.f;
+          c += on ? __fdividef(1.0f, S[i]) : 0.f;
+          cl[i] = c;
         }
         const float cpre = group_excl_prefix<LPL>(c, gl);
         nll = group_sum<LPL>(nll);
@@ -292,8 +316,7 @@ __global__ void __launch_bounds__(256) lists_large_kernel(const ListParams P) {
             float* gr = P.grad + map_off;
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
-              if (gl * IPL + i < K && !((inval >> i) & 1u))
-                red_add_f32(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
+              if (((emask & ~inval) >> i) & 1u) red_add_f32(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
           }
         }
       }

@@ -65,6 +65,28 @@ def test_philox_draws_and_rankings(cuda_device, K):
         assert np.array_equal(rank[b], want)
 
 
+@pytest.mark.parametrize("K", [5, 20])
+def test_philox_redraw_path_on_large_maps(cuda_device, K):
+    """M = 3 M valid pixels (2^32 mod M = 1 967 296): Lemire's rejection fires about once per 2200
+    draws, so the redraw stream (word block 0x8000 | ...) is exercised and must match the model."""
+    from pldepth_b200 import ops
+    H, W = 1500, 2000
+    n = 12000 if K == 5 else 3000
+    rs = np.random.RandomState(1)
+    gt = rs.rand(1, H, W).astype(np.float32)
+    mask = np.ones((1, H, W), np.float32)
+    vf, nv = ops.mask_compact(torch.from_numpy(mask).to(cuda_device), H, W)
+    M = abs(int(nv[0].item()))
+    assert M == H * W
+    _, sel = ops.sample_lists_philox(torch.from_numpy(gt).to(cuda_device), vf, nv, K, n, 99, 0, 0, want_sel=True,
+                                     want_rankings=False)
+    want = pm.draw_selection(99, 0, 0, n, K, M)
+    thresh = ((1 << 32) - M) % M
+    low = (pm.philox4x32_10(np.arange(n, dtype=np.uint32), 0, 0, 0, 99, 0)[0].astype(np.uint64) * np.uint64(M)) & np.uint64(0xFFFFFFFF)
+    assert thresh == 1967296 and (low < thresh).sum() > 0        # the redraw path really runs
+    assert np.array_equal(sel[0].cpu().numpy(), want)
+
+
 def test_philox_is_independent_of_batch_split(cuda_device):
     from pldepth_b200 import ops
     H, W, K, n = 32, 32, 5, 300

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library loads and exports exactly what include/pldepth_b200.h declares
+(no compute calls -- there is no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pldepth_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pld_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("pld_ctx_create", "pld_mask_compact", "pld_sample_lists_philox", "pld_sample_lists_fed",
+                 "pld_sample_lists_mt", "pld_mt19937_generate", "pld_score_lists", "pld_select_top",
+                 "pld_listmle_fwd_bwd", "pld_fused_sample_loss_bwd", "pld_fused_step", "pld_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol_and_binding_is_complete():
+    from pldepth_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.fail("libpldepth_b200.so is not built; run __graft_entry__.build()")
+    lib = _lib.load_library()
+    syms = declared_symbols()
+    for s in syms:
+        assert hasattr(lib, s), "library does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
+    assert lib.pld_version() >= 100
+    assert lib.pld_launch_count() == 0
+
+
+def test_header_cites_reference_lines():
+    src = open(HEADER).read()
+    for cite in ("sampling.py:135", "sampling.py:110-145", "depth_utils.py:39-61", "nll_loss.py:43-62",
+                 "sampling.py:161-169", "depth_utils.py:5-21"):
+        assert cite in src
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from pldepth_b200 import _lib
+    with pytest.raises(_lib.PLDError):
+        _lib.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pldepth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

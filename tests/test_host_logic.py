@@ -1,0 +1,71 @@
+"""CPU: host-side mirrors of the reference interface (no GPU needed)."""
+import numpy as np
+import pytest
+
+from pldepth_b200 import losses, sampling
+from pldepth_b200.models_meta import ModelParameters
+
+
+def test_model_parameters_bag():
+    mp = ModelParameters(ranking_size=5)
+    assert mp.get_parameter("ranking_size") == 5
+    assert mp.get_parameter("missing") is None and mp.get_parameter("missing", 3) == 3
+    mp.set_parameter("batch_size", 4)
+    dup = mp.duplicate()
+    dup.set_parameter("batch_size", 8)
+    assert mp.get_parameter("batch_size") == 4
+    assert "ranking_size_5" in mp.get_parameter_string()
+
+
+@pytest.mark.parametrize("cls,factor", [("PurelyMaskedRandomSamplingStrategy", 0.8),
+                                        ("MaskedRandomSamplingStrategy", 1.5),
+                                        ("ThresholdedMaskedRandomSamplingStrategy", 1.5),
+                                        ("InformationScoreBasedSampling", 5)])
+def test_sampler_construction_mirrors_reference(cls, factor):
+    mp = ModelParameters(ranking_size=7, downscaling_factor=2)
+    s = getattr(sampling, cls)(mp)
+    assert s.num_points_per_sample == 7
+    assert s.downscaling_factor == 2
+    assert s.threshold == 0.03
+    assert s._default_factor == factor
+    assert cls in str(s) and "num_points_per_sample=7" in str(s)
+    s.num_points_per_sample = 9
+    assert s.num_points_per_sample == 9
+    assert s.determine_x_y_scales(np.zeros((8, 6, 3)), np.zeros((4, 3))) == (2.0, 2.0)
+
+
+def test_thresholded_positional_threshold_like_the_provider():
+    # hourglass_provider.py:21 passes the threshold positionally
+    s = sampling.ThresholdedMaskedRandomSamplingStrategy(ModelParameters(ranking_size=3), 0.05)
+    assert s.threshold == 0.05 and s.equality_penalty == -1000
+    with pytest.raises(ValueError):
+        sampling.PurelyMaskedRandomSamplingStrategy(ModelParameters(ranking_size=3), rng="xorshift")
+
+
+def test_unmasked_sampling_is_out_of_scope():
+    s = sampling.RandomSamplingStrategy(ModelParameters(ranking_size=3))
+    with pytest.raises(NotImplementedError):
+        s.sample_points(None, None)
+
+
+def test_loss_constructor_contract():
+    fn = losses.HourglassNegativeLogLikelihood(ranking_size=5, batch_size=4, debug=False)
+    assert fn.reduction == "auto" and fn.get_config()["ranking_size"] == 5
+    with pytest.raises(NotImplementedError):
+        losses.HourglassNegativeLogLikelihood(5, 4, lambda_weight=1)
+    with pytest.raises(ValueError):
+        losses.HourglassNegativeLogLikelihood(5, 4, reduction="median")
+    with pytest.raises(ValueError):
+        losses.HourglassNegativeLogLikelihood(0, 4)
+
+    class FakeReduction(object):        # tf.losses.Reduction members carry a .name
+        name = "SUM_OVER_BATCH_SIZE"
+    assert losses.HourglassNegativeLogLikelihood(5, 4, reduction=FakeReduction()).reduction == "sum_over_batch_size"
+
+
+def test_no_cpu_fallback():
+    import torch
+    from pldepth_b200 import ops
+    from pldepth_b200._lib import PLDError
+    with pytest.raises(PLDError):
+        ops.as_cuda(torch.zeros(3), torch.float32, "x")

@@ -308,44 +308,44 @@ def run_b200(args):
         pass
 
     # ---- end to end through the public API with HOST buffers ---------------------------------
-    e2e = None
-    if rank == 0 or world > 1:
-        gt_p = torch.from_numpy(gt_h).pin_memory()
-        mask_p = torch.from_numpy(mask_h).pin_memory()
-        pred_p = torch.from_numpy(pred_h).pin_memory()
-        grad_p = torch.empty((B, H, W, 1), dtype=torch.float32).pin_memory()
-        loss_p = torch.empty(1, dtype=torch.float32).pin_memory()
-        d_gt, d_mask, d_pred = sets[0]["gt"], sets[0]["mask"], sets[0]["pred"]
+    # HostPipelinedStep: every step copies its gt / mask / pred from pinned host memory, runs the
+    # fused step and copies loss + dense gradient back; copies of neighbouring steps overlap kernels.
+    from pldepth_b200.step import HostPipelinedStep
+    gt_p = [torch.from_numpy(np.roll(gt_h, s, axis=0)).pin_memory() for s in range(2)]
+    mask_p = torch.from_numpy(mask_h).pin_memory()
+    pred_p = [torch.from_numpy(np.roll(pred_h, s, axis=0)).pin_memory() for s in range(2)]
+    runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B)
+    red_buf = torch.zeros(1, dtype=torch.float64, device=dev)
 
-        def e2e_step(i):
-            d_gt.copy_(gt_p, non_blocking=True)
-            d_mask.copy_(mask_p, non_blocking=True)
-            d_pred.copy_(pred_p, non_blocking=True)
-            out = step.run(d_gt, d_mask, d_pred, out=sets[0]["out"])
-            if world > 1:
-                dist.all_reduce(out["loss_sum"])
-            loss_p.copy_(out["loss"], non_blocking=True)
-            grad_p.copy_(out["grad"], non_blocking=True)
-
-        n_e2e = max(3, min(args.steps, 10))
-        for i in range(3):
-            e2e_step(i)
-        barrier()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(n_e2e):
-            e2e_step(i)
-        b_.record()
-        barrier()
-        ms_e2e = a.elapsed_time(b_)
+    def e2e_step(i):
+        t = runner.submit(gt_p[i % 2], mask_p, pred_p[i % 2])
         if world > 1:
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": L * world * n_e2e / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(gt_p.numel() + mask_p.numel() + pred_p.numel()) * 4,
-               "d2h_bytes_per_step": int(grad_p.numel() + 1) * 4, "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
-               "api": "FusedPLStep.run on pinned host gt/mask/pred; loss + dense gradient copied back"}
+            dist.all_reduce(runner.slots[t % 2]["out"]["loss_sum"])
+        return t
+
+    n_e2e = max(3, min(args.steps, 20))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    last = 0
+    for i in range(n_e2e):
+        last = e2e_step(i)
+    loss_host, grad_host = runner.result(last)          # waits for the final D2H
+    b_.record()
+    barrier()
+    ms_e2e = a.elapsed_time(b_)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    h2d, d2h = runner.bytes_per_step()
+    e2e = {"value": L * world * n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
+           "api": "HostPipelinedStep.submit/result: pinned host gt+mask+pred -> device, fused step, loss + dense "
+                  "gradient -> pinned host; 2 slots, H2D / compute / D2H streams overlap across steps",
+           "last_loss": loss_host}
 
     if rank == 0:
         line = {

@@ -88,3 +88,83 @@ class FusedPLStep(object):
 
     def check(self, dev):
         return ops.check_status(dev)
+
+
+class HostPipelinedStep(object):
+    """The same step fed from HOST buffers (NumPy / pinned tensors), as the reference's tf.data
+    pipeline feeds Keras: inputs are copied host->device, the fused step runs, loss and dense
+    gradient are copied back.  Two device/host slots and three streams (H2D, compute, D2H) let the
+    copies of step i+1 and i-1 overlap the kernels of step i; PCIe is full duplex.
+
+        runner = HostPipelinedStep(K, R, B, H, W)
+        for batch in data:                       # gt, mask, pred: float32 host arrays
+            ticket = runner.submit(gt, mask, pred)
+        loss, grad = runner.result(ticket)       # waits for that step only
+    """
+
+    def __init__(self, ranking_size, rankings_per_image, B, H, W, Hm=None, Wm=None, seed=0, device=None,
+                 emit_rankings=True, global_batch=None, image_base=0, slots=2):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        Hm, Wm = Hm or H, Wm or W
+        self.dev = dev
+        self.shape = (B, H, W, Hm, Wm)
+        self.step = FusedPLStep(ranking_size, rankings_per_image, seed, emit_rankings, global_batch, image_base)
+        self.slots = []
+        for _ in range(slots):
+            self.slots.append(dict(
+                gt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
+                mask=torch.empty((B, Hm, Wm), dtype=torch.float32, device=dev),
+                pred=torch.empty((B, H, W, 1), dtype=torch.float32, device=dev),
+                out=FusedPLStep.new_buffers(B, H, W, Hm, Wm, rankings_per_image, ranking_size, dev, emit_rankings),
+                h_loss=torch.empty(1, dtype=torch.float32).pin_memory(),
+                h_grad=torch.empty((B, H, W, 1), dtype=torch.float32).pin_memory(),
+                ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), used=False))
+        self.s_in = torch.cuda.Stream(dev)
+        self.s_out = torch.cuda.Stream(dev)
+        self.count = 0
+
+    @staticmethod
+    def _host(x):
+        if isinstance(x, torch.Tensor):
+            return x
+        import numpy as np
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+
+    def submit(self, gt, mask, pred):
+        i = self.count
+        sl = self.slots[i % len(self.slots)]
+        compute = torch.cuda.current_stream(self.dev)
+        gt, mask, pred = self._host(gt), self._host(mask), self._host(pred)
+        with torch.cuda.stream(self.s_in):
+            if sl["used"]:
+                self.s_in.wait_event(sl["ev_done"])      # the slot's previous kernels have consumed the inputs
+            sl["gt"].copy_(gt.reshape(sl["gt"].shape), non_blocking=True)
+            sl["mask"].copy_(mask.reshape(sl["mask"].shape), non_blocking=True)
+            sl["pred"].copy_(pred.reshape(sl["pred"].shape), non_blocking=True)
+            sl["ev_in"].record(self.s_in)
+        compute.wait_event(sl["ev_in"])
+        if sl["used"]:
+            compute.wait_event(sl["ev_out"])             # previous results of this slot have left the device
+        out = self.step.run(sl["gt"], sl["mask"], sl["pred"], out=sl["out"])
+        sl["ev_done"].record(compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["ev_done"])
+            sl["h_loss"].copy_(out["loss"], non_blocking=True)
+            sl["h_grad"].copy_(out["grad"], non_blocking=True)
+            sl["ev_out"].record(self.s_out)
+        sl["used"] = True
+        self.count += 1
+        return i
+
+    def result(self, ticket):
+        """(loss float, grad pinned tensor [B,H,W,1]) of step ``ticket`` (must be one of the last
+        ``slots`` submitted steps); blocks until its copies have landed."""
+        if ticket < self.count - len(self.slots) or ticket >= self.count:
+            raise ValueError("result of step %d is no longer (or not yet) available" % ticket)
+        sl = self.slots[ticket % len(self.slots)]
+        sl["ev_out"].synchronize()
+        return float(sl["h_loss"][0]), sl["h_grad"]
+
+    def bytes_per_step(self):
+        B, H, W, Hm, Wm = self.shape
+        return (2 * B * H * W + B * Hm * Wm) * 4, (B * H * W + 1) * 4

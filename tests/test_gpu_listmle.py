@@ -219,3 +219,28 @@ def test_full_size_config2_properties(cuda_device):
     sub = rank[5, pick].cpu().numpy()[None]
     _, _, want_pl = lo.hourglass_nll(sub, pred[5:6], 1, K)
     assert_close(per_list.reshape(B, R)[5, pick].cpu().numpy(), want_pl, "per-list NLL at full size")
+
+
+def test_host_pipelined_step_matches_device_step(cuda_device):
+    """HostPipelinedStep (pinned host in, loss + gradient out, overlapped copies) returns, step by
+    step, what FusedPLStep computes on device-resident inputs."""
+    from pldepth_b200.step import FusedPLStep, HostPipelinedStep
+    from tests.test_gpu_sampler import make_maps
+    B, H, W, K, R = 3, 32, 40, 5, 700
+    runner = HostPipelinedStep(K, R, B, H, W, seed=11, device=cuda_device)
+    ref = FusedPLStep(K, R, seed=11)
+    tickets, wants = [], []
+    for i in range(5):
+        gt, mask = make_maps(H, W, H, W, 50 + i, B)
+        pred = np.random.RandomState(i).randn(B, H, W, 1).astype(np.float32)
+        tickets.append(runner.submit(gt, mask, pred))
+        out = ref.run(*(torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred)))
+        wants.append((out["loss"].item(), out["grad"].cpu().numpy().copy()))
+        if i >= 1:                                  # results stay available for `slots` steps
+            loss, grad = runner.result(tickets[i - 1])
+            assert loss == wants[i - 1][0]
+            assert_close(grad.numpy(), wants[i - 1][1], "pipelined gradient")
+    loss, grad = runner.result(tickets[-1])
+    assert loss == wants[-1][0]
+    with pytest.raises(ValueError):
+        runner.result(tickets[0])

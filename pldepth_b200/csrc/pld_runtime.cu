@@ -143,28 +143,29 @@ __global__ void __launch_bounds__(MC_THREADS) mask_scatter_kernel(
       return;
     }
   }
-  const int base = chunk * MC_CHUNK + threadIdx.x * MC_ITEMS;
-  const uint32_t f = (base < Nm) ? mask_flags16(m, base, Nm) : 0u;
-  const int c = __popc(f);
-  // block exclusive scan of c
-  int inc = c;
+  // lane-consecutive pixels + ballots: coalesced mask reads and table writes (see prep_build_kernel)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wbase = chunk * MC_CHUNK + wid * (MC_ITEMS * 32);
+  uint32_t bal[MC_ITEMS];
+  int wcount = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+  for (int i = 0; i < MC_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    const bool v = (idx < Nm) && (__ldg(m + idx) > 0.f);
+    bal[i] = __ballot_sync(0xffffffffu, v);
+    wcount += __popc(bal[i]);
   }
   __syncthreads();
-  if (lane == 31) s_warp[wid] = inc;
+  if (lane == 0) s_warp[wid] = wcount;
   __syncthreads();
-  int woff = 0;
-  for (int i = 0; i < wid; ++i) woff += s_warp[i];
-  int rank = s_prefix + woff + inc - c;
+  int rank = s_prefix;
+  for (int i = 0; i < wid; ++i) rank += s_warp[i];
+  const uint32_t lt = (1u << lane) - 1u;
   int32_t* out = valid_flat + (size_t)b * Nm;
 #pragma unroll
   for (int i = 0; i < MC_ITEMS; ++i) {
-    if ((f >> i) & 1u) {
-      const int idx = base + i;
+    if ((bal[i] >> lane) & 1u) {
+      const int idx = wbase + i * 32 + lane;
       int p;
       if (identity) {
         p = idx;
@@ -172,10 +173,11 @@ __global__ void __launch_bounds__(MC_THREADS) mask_scatter_kernel(
         const int rm = idx / Wm, cm = idx - rm * Wm;
         p = (int)((double)rm * xs) * W + (int)((double)cm * ys);
       }
-      out[rank++] = p;
+      out[rank + __popc(bal[i] & lt)] = p;
     }
+    rank += __popc(bal[i]);
   }
-  if (chunk == nchunks - 1 && threadIdx.x == MC_THREADS - 1) {
+  if (chunk == nchunks - 1 && threadIdx.x == 0) {
     int t = 0;
     for (int i = 0; i < MC_THREADS / 32; ++i) t += s_warp[i];
     n_valid[b] = s_prefix + t;

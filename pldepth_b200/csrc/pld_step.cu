@@ -87,7 +87,6 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   const int prefix = block_sum_int(pre, s_warp);
   float2* tab = table + (size_t)b * table_stride;
   const float* g = gt + (size_t)b * HW;
-  const int base = chunk * PC_CHUNK + threadIdx.x * PC_ITEMS;
   if (identity_scale && total == Nm) {
     const float* s = pred + (size_t)b * HW;
     // coalesced: thread t handles elements chunk*CHUNK + i*THREADS + t
@@ -99,26 +98,31 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
     return;
   }
+  // Compaction with lane-consecutive pixels: warp w of the CTA owns pixels
+  // [chunk*CHUNK + w*512, +512) as 16 rows of 32; ballots give each valid pixel its rank, so mask
+  // reads, gt reads and table writes are all coalesced.
   const float* m = mask + (size_t)b * Nm;
-  const uint32_t f = (base < Nm) ? flags16(m, base, Nm) : 0u;
-  const int c = __popc(f);
-  int inc = c;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();
-  if (lane == 31) s_warp[wid] = inc;
-  __syncthreads();
-  int woff = 0;
-  for (int i = 0; i < wid; ++i) woff += s_warp[i];
-  int rank = prefix + woff + inc - c;
+  const int wbase = chunk * PC_CHUNK + wid * (PC_ITEMS * 32);
+  uint32_t bal[PC_ITEMS];
+  int wcount = 0;
 #pragma unroll
   for (int i = 0; i < PC_ITEMS; ++i) {
-    if ((f >> i) & 1u) {
-      const int idx = base + i;
+    const int idx = wbase + i * 32 + lane;
+    const bool v = (idx < Nm) && (__ldg(m + idx) > 0.f);
+    bal[i] = __ballot_sync(0xffffffffu, v);
+    wcount += __popc(bal[i]);
+  }
+  __syncthreads();
+  if (lane == 0) s_warp[wid] = wcount;
+  __syncthreads();
+  int rank = prefix;
+  for (int i = 0; i < wid; ++i) rank += s_warp[i];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < PC_ITEMS; ++i) {
+    if ((bal[i] >> lane) & 1u) {
+      const int idx = wbase + i * 32 + lane;
       int p;
       if (identity_scale) {
         p = idx;
@@ -126,8 +130,9 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
         const int rm = idx / Wm, cm = idx - rm * Wm;
         p = (int)((double)rm * xs) * W + (int)((double)cm * ys);  // sampling.py:115-119
       }
-      tab[rank++] = make_float2(__int_as_float(p), __ldg(g + p));
+      tab[rank + __popc(bal[i] & lt)] = make_float2(__int_as_float(p), __ldg(g + p));
     }
+    rank += __popc(bal[i]);
   }
   if (chunk == 0 && threadIdx.x == 0) n_valid[b] = total;
 }

@@ -210,3 +210,38 @@ def test_single_valid_pixel_consumes_no_words(cuda_device):
     st1 = np.random.get_state()
     assert out.shape == (8, 3, 2) and (out[:, :, 0] == 21).all() and (out[:, :, 1] == gt[2, 5]).all()
     assert np.array_equal(st0[1], st1[1]) and st0[2] == st1[2]
+
+
+def test_provider_mirror_per_image_and_batched(cuda_device):
+    """HourglassLargeScaleDataProvider.sample_rankings keeps the reference's per-image contract and
+    reproduces a golden case; the batched device path returns the (B, R, K, 2) tensor the reference's
+    map + batch would."""
+    from pldepth_b200 import sampling
+    from pldepth_b200.models_meta import ModelParameters
+    from pldepth_b200.provider import HourglassLargeScaleDataProvider
+    c = load_case([p for p in GOLDEN if "thresholded_k5" in p][0])
+    mp = ModelParameters(ranking_size=c["K"], rankings_per_image=c["R"], batch_size=2, val_rankings_per_img=7)
+    mp.set_parameter("sampling_strategy", sampling.ThresholdedMaskedRandomSamplingStrategy(mp))
+    prov = HourglassLargeScaleDataProvider(mp, None, None)
+    H, W = c["gt"].shape
+    image = np.zeros((H, W, 3), np.float64)
+    np.random.seed(c["seed"])
+    img_out, rank = prov.sample_rankings(image, c["mask"], c["gt"])
+    assert img_out.dtype == np.float32 and rank.dtype == np.float32
+    assert np.array_equal(rank, c["rankings"])
+    val = prov.generate_validation_rankings([(image, c["mask"], c["gt"])] * 3)
+    assert val.shape == (3, 7, c["K"], 2) and (np.diff(val[..., 1], axis=-1) <= 0).all()
+    # batched, philox
+    mp2 = ModelParameters(ranking_size=5, rankings_per_image=64, batch_size=3)
+    mp2.set_parameter("sampling_strategy", sampling.InformationScoreBasedSampling(mp2, rng="philox", seed=3))
+    prov2 = HourglassLargeScaleDataProvider(mp2, augmentation=True)
+    gts = [c["gt"]] * 7
+    masks = [c["mask"]] * 7
+    images = [image] * 7
+    it = prov2.iterate_train_batches(images, masks, gts, cuda_device, repeat=False)
+    batches = list(it)
+    assert len(batches) == 2                                # drop_remainder: 7 // 3
+    img_b, y_true = batches[0]
+    assert tuple(img_b.shape) == (3, H, W, 3) and tuple(y_true.shape) == (3, 64, 5, 2)
+    d = y_true[..., 1]
+    assert bool((d[:, :, :-1] >= d[:, :, 1:]).all())

@@ -189,6 +189,17 @@ int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float
                    float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
                    float* per_list, float* grad, void* stream);
 
+/* ---- evaluation metrics next to the training step ------------------------------
+ * ordinal_error (pldepth/active_learning/metrics.py:60-70): pred, gt f32[N,HW]; idx0, idx1 i32[num] are
+ * the fixed pixel pairs (np.random.seed(10); np.random.choice(HW, 2*num, replace=False), split in two);
+ * err[i] = 1 - (# pairs with (pred[a] > pred[b]) == (gt[a] > gt[b])) / num.
+ * calc_d / nDCG (metrics.py:92-110): ids i32[n] the fixed sample (seed 69), n <= 1024;
+ * out[i] = DCG(sorted 1/(minmax(pred)[ids]+1)) / DCG(sorted 1/(gt[ids]+1)). */
+int pld_ordinal_error(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* idx0, const int32_t* idx1,
+                      int N, int HW, int num, float* err, void* stream);
+int pld_ndcg(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* ids, int N, int HW, int n, float* out,
+             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

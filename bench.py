@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5s"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5s", "C5"])
     ap.add_argument("--sets", type=int, default=4, help="rotating input/output buffer sets (> L2 in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for cpu_baseline")
@@ -47,8 +47,10 @@ def parse_args():
 
 def workload_shape(name):
     from pldepth_b200 import synth
-    if name == "C5s":   # one GPU's share of config 5 at 8 GPUs, scaled to fit a quick run
+    if name == "C5s":   # a quarter of one GPU's share of config 5 at 8 GPUs (quick run)
         return dict(B=8, H=1024, W=768, K=10, R=1000000)
+    if name == "C5":    # one GPU's share of config 5 at 8 GPUs: 32 of the 256 images
+        return dict(B=32, H=1024, W=768, K=10, R=1000000)
     return dict(synth.CONFIGS[name])
 
 
@@ -205,7 +207,7 @@ def run_b200(args):
     B, H, W, K, R = shape["B"], shape["H"], shape["W"], shape["K"], shape["R"]
     HW, L = H * W, B * R
     n_sets = max(1, args.sets)
-    cfg_id = {"C1": 1, "C2": 2, "C3": 3, "C5s": 5}[args.workload]
+    cfg_id = {"C1": 1, "C2": 2, "C3": 3, "C5s": 5, "C5": 5}[args.workload]
 
     # synthetic maps: a few distinct rank-transformed fields, rolled to make B distinct images
     base_maps = [synth.depth_map(H, W, 1000 * cfg_id + 17 * rank + i) for i in range(min(B, 4))]

@@ -72,6 +72,12 @@ int pld_ctx_destroy(pld_ctx* ctx);
  * them.  This is how data errors that the reference reports as Python exceptions surface. */
 int pld_ctx_status(pld_ctx* ctx, void* stream, int* status_host);
 
+/* Deterministic mode (off by default): gradient contributions are accumulated with 64-bit fixed-point
+ * (2^-32) integer atomics in context scratch and converted once, so the dense gradient is
+ * bit-reproducible run to run and independent of launch geometry (float atomics are not).  Costs an
+ * extra 8 B/pixel scratch, a memset and a conversion pass. */
+int pld_ctx_set_deterministic(pld_ctx* ctx, int on);
+
 /* Measurement hook: with slots > 0 the library records a CUDA event pair on the launch stream
  * around every list-kernel launch (the dominant kernel of each entry point below) into a ring of
  * `slots` pairs; pld_ctx_kernel_times waits for them, returns the durations in ms and resets the

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pld_ctx_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "pld_ctx_destroy": (c_int, [c_void_p]),
     "pld_ctx_status": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
+    "pld_ctx_set_deterministic": (c_int, [c_void_p, c_int]),
     "pld_ctx_kernel_timing": (c_int, [c_void_p, c_int]),
     "pld_ctx_kernel_times": (c_int, [c_void_p, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_int)]),
     "pld_mask_compact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -130,6 +131,10 @@ class Context(object):
         s = c_int(0)
         check(self.lib.pld_ctx_status(self.handle, c_void_p(stream_ptr), ctypes.byref(s)))
         return s.value
+
+    def set_deterministic(self, on=True):
+        """Bit-reproducible gradients (64-bit fixed-point accumulation) for this context."""
+        check(self.lib.pld_ctx_set_deterministic(self.handle, 1 if on else 0))
 
     def kernel_timing(self, slots):
         check(self.lib.pld_ctx_kernel_timing(self.handle, int(slots)))

@@ -4,6 +4,7 @@
 namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
+int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
 int mt_compact_images(pld_ctx* ctx, const int32_t* n_valid, int B, int need_per_image, const uint32_t* raw,
                       int64_t n_raw, int64_t* consumed_io, int32_t* sel_out, cudaStream_t st);
 
@@ -21,8 +22,15 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
     int rc = ctx->ensure_partials(per_image_cap * P.B + P.B);
     if (rc) return rc;
     P.partials = ctx->d_partials;
-    if (P.grad != nullptr && !accumulate)
-      PLD_CUDA(cudaMemsetAsync(P.grad, 0, sizeof(float) * (size_t)P.B * (size_t)P.HW, st));
+    const size_t gn = (size_t)P.B * (size_t)P.HW;
+    if (P.grad != nullptr && ctx->deterministic) {
+      int rc2 = ctx->ensure_acc(gn);
+      if (rc2) return rc2;
+      P.acc = ctx->d_acc;
+      PLD_CUDA(cudaMemsetAsync(P.acc, 0, sizeof(long long) * gn, st));
+    } else if (P.grad != nullptr && !accumulate) {
+      PLD_CUDA(cudaMemsetAsync(P.grad, 0, sizeof(float) * gn, st));
+    }
   }
   if (P.n == 0) {
     if (loss) {
@@ -35,6 +43,8 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
   int rc = (P.K <= 16) ? launch_lists_small(P, src, loss, ctx->num_sms, st)
                        : launch_lists_large(P, src, loss, ctx->num_sms, st);
   ctx->time_end(st);
+  if (rc == PLD_OK && P.acc != nullptr)
+    rc = launch_acc_finalize(ctx, P.grad, (size_t)P.B * (size_t)P.HW, P.scale, accumulate, st);
   return rc;
 }
 

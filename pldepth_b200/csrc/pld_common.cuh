@@ -60,6 +60,10 @@ struct pld_ctx {
   cudaEvent_t* ev_start;
   cudaEvent_t* ev_stop;
   int ev_cap, ev_count;
+  int deterministic;     // 1: gradients accumulate in 64-bit fixed point (bit-reproducible)
+  long long* d_acc;
+  size_t acc_cap;
+  int ensure_acc(size_t elems);
   int ensure_scratch(size_t bytes);
   int ensure_partials(int n);
   inline void time_begin(cudaStream_t st) { if (ev_cap > 0 && ev_count < ev_cap) cudaEventRecord(ev_start[ev_count], st); }

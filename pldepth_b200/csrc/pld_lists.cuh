@@ -19,6 +19,7 @@ struct ListParams {
   int32_t* sel_out;            // [B, n, K] nullable
   float* per_list;             // [B*n] nullable
   float* grad;                 // [B, HW] nullable
+  long long* acc;              // [B, HW] fixed-point (2^-32) accumulators: deterministic mode, else null
   float* loss;                 // [1]
   double* loss_sum;            // [1] nullable
   double* partials;
@@ -39,6 +40,17 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 #else
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 #endif
+}
+
+// gradient contribution of one point: float RED (fast) or 64-bit fixed-point atomic (integer addition is
+// associative, so the dense gradient is bit-reproducible); `g` is the unscaled d nll / d score
+__device__ __forceinline__ void grad_add(const ListParams& P, size_t idx, float g) {
+  if (P.acc != nullptr) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.acc) + idx,
+              (unsigned long long)__double2ll_rn((double)g * 4294967296.0));
+  } else {
+    red_add_f32(P.grad + idx, g * P.scale);
+  }
 }
 
 // compare-exchange, descending (a >= b afterwards)

@@ -313,10 +313,9 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
             if (P.per_list != nullptr) P.per_list[list_id] = nll;
           }
           if (P.grad != nullptr) {
-            float* gr = P.grad + map_off;
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
-              if (((emask & ~inval) >> i) & 1u) red_add_f32(gr + p[i], (ex[i] * (cl[i] + cpre) - 1.0f) * P.scale);
+              if (((emask & ~inval) >> i) & 1u) grad_add(P, map_off + (size_t)p[i], ex[i] * (cl[i] + cpre) - 1.0f);
           }
         }
       }

@@ -241,10 +241,9 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           local += nll;
           if (P.per_list != nullptr) P.per_list[list_id] = nll;
           if (P.grad != nullptr) {
-            float* gr = P.grad + map_off;
 #pragma unroll
             for (int k = 0; k < K; ++k)
-              if (!((inval >> k) & 1u)) red_add_f32(gr + p[k], g[k] * P.scale);
+              if (!((inval >> k) & 1u)) grad_add(P, map_off + (size_t)p[k], g[k]);
           }
         }
       }

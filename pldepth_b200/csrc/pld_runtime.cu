@@ -40,6 +40,23 @@ int pld_ctx::ensure_scratch(size_t bytes) {
   return PLD_OK;
 }
 
+int pld_ctx::ensure_acc(size_t elems) {
+  if (elems <= acc_cap) return PLD_OK;
+  if (d_acc) {
+    cudaDeviceSynchronize();
+    cudaFree(d_acc);
+    d_acc = nullptr;
+    acc_cap = 0;
+  }
+  if (cudaMalloc(&d_acc, sizeof(long long) * elems) != cudaSuccess) {
+    cudaGetLastError();
+    pld::set_error("accumulator allocation failed");
+    return PLD_ENOMEM;
+  }
+  acc_cap = elems;
+  return PLD_OK;
+}
+
 int pld_ctx::ensure_partials(int n) {
   if (n <= partials_cap) return PLD_OK;
   if (d_partials) {
@@ -375,6 +392,22 @@ __global__ void __launch_bounds__(MTC_THREADS) mt_scatter_kernel(
 
 __global__ void copy_i64_kernel(const long long* src, long long* dst) { *dst = *src; }
 
+// deterministic mode: fixed-point accumulators -> float gradient (grad = [grad +] acc * 2^-32 * scale)
+__global__ void __launch_bounds__(256) acc_finalize_kernel(const long long* __restrict__ acc, float* __restrict__ grad,
+                                                           size_t n, float scale, int accumulate) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float v = (float)((double)acc[i] * (1.0 / 4294967296.0) * (double)scale);
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st) {
+  int gx = (int)((n + 255) / 256);
+  if (gx > ctx->num_sms * 16) gx = ctx->num_sms * 16;
+  acc_finalize_kernel<<<gx, 256, 0, st>>>(ctx->d_acc, grad, n, scale, accumulate);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // gt min / max per image
 // ------------------------------------------------------------------------------------------
@@ -616,8 +649,15 @@ int pld_ctx_destroy(pld_ctx* ctx) {
   cudaFree(ctx->d_ticket);
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_acc);
   pld_ctx_kernel_timing(ctx, 0);
   delete ctx;
+  return PLD_OK;
+}
+
+int pld_ctx_set_deterministic(pld_ctx* ctx, int on) {
+  PLD_REQUIRE(ctx != nullptr, "null context");
+  ctx->deterministic = on ? 1 : 0;
   return PLD_OK;
 }
 

@@ -15,6 +15,7 @@
 
 namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
+int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_ITEMS = 16;
@@ -198,8 +199,15 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
+  if (grad != nullptr && ctx->deterministic) {
+    rc = ctx->ensure_acc(gtotal);
+    if (rc) return rc;
+    P.acc = ctx->d_acc;
+    PLD_CUDA(cudaMemsetAsync(P.acc, 0, sizeof(long long) * gtotal, st));
+  }
   ctx->time_begin(st);
   rc = launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
+  if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   return rc;
 }

@@ -244,3 +244,33 @@ def test_host_pipelined_step_matches_device_step(cuda_device):
     assert loss == wants[-1][0]
     with pytest.raises(ValueError):
         runner.result(tickets[0])
+
+
+def test_deterministic_mode_is_bit_reproducible(cuda_device):
+    """With pld_ctx_set_deterministic the dense gradient is identical run to run, identical between the
+    one-call step and the staged calls (different kernels / launch geometry), and still within
+    tolerance of the oracle."""
+    from pldepth_b200 import ops
+    from pldepth_b200._lib import Context
+    from tests.test_gpu_sampler import make_maps
+    B, H, W, K, n = 3, 48, 40, 5, 4000          # 60k points on 1920 pixels: heavy accumulation per pixel
+    gt, mask = make_maps(H, W, H, W, 21, B)
+    pred = np.random.RandomState(3).randn(B, H, W, 1).astype(np.float32)
+    gt_d, pred_d, mask_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, pred, mask))
+    ctx = Context.current(cuda_device.index or 0)
+    ctx.set_deterministic(True)
+    try:
+        grads = []
+        for _ in range(3):
+            _, _, g, rank, _, _ = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=8)
+            grads.append(g.clone())
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+        vf, nv = ops.mask_compact(mask_d, H, W)
+        _, _, g2, rank2, _ = ops.fused_sample_loss_bwd(gt_d, vf, nv, pred_d, K, n, seed=8)
+        assert torch.equal(rank, rank2) and torch.equal(grads[0], g2)
+        _, _, g3, _ = ops.listmle_fwd_bwd(rank, pred_d, B, K, 1.0 / (B * n))
+        assert torch.equal(grads[0], g3)
+        _, want_grad, _ = lo.hourglass_nll(rank.cpu().numpy(), pred, B, K)
+        assert_close(grads[0].cpu().numpy(), want_grad, "deterministic gradient")
+    finally:
+        ctx.set_deterministic(False)

@@ -3,8 +3,6 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "pld_common.cuh"
 
 namespace pld {
@@ -570,23 +568,18 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// top-R selection: ascending stable radix sort of (ordered score) then of the image id;
-// the kept lists are the last R of each image's run, read backwards.
+// top-R selection (staged API): per-image ascending stable radix sort of the ordered scores
+// (pld_sort.cu); the kept lists are the last R of each image's run, read backwards.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) select_keys_kernel(const double* __restrict__ scores,
-                                                          size_t total, uint64_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ vals) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    double s = scores[i];
+__global__ void __launch_bounds__(256) select_keys_kernel(const double* __restrict__ scores, int n,
+                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t off = (size_t)blockIdx.y * n;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    double s = scores[off + i];
     if (s == 0.0) s = 0.0;  // -0.0 == +0.0 for argsort
-    keys[i] = double_to_ordered(s);
-    vals[i] = (uint32_t)i;
+    keys[off + i] = double_to_ordered(s);
+    vals[off + i] = (uint32_t)i;
   }
-}
-__global__ void __launch_bounds__(256) select_image_kernel(const uint32_t* __restrict__ vals, size_t total,
-                                                           uint32_t n, uint16_t* __restrict__ img) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
-    img[i] = (uint16_t)(vals[i] / n);
 }
 __global__ void __launch_bounds__(256) select_gather_kernel(const uint32_t* __restrict__ vals,
                                                             const float* __restrict__ rankings, int n,
@@ -596,13 +589,17 @@ __global__ void __launch_bounds__(256) select_gather_kernel(const uint32_t* __re
   const int b = blockIdx.y;
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < R; j += gridDim.x * warps) {
-    const uint32_t src = vals[(size_t)b * n + (size_t)(n - 1 - j)];  // global candidate index
-    const float2* s = reinterpret_cast<const float2*>(rankings) + (size_t)src * K;
+    const uint32_t src = vals[(size_t)b * n + (size_t)(n - 1 - j)];  // candidate index inside image b
+    const float2* s = reinterpret_cast<const float2*>(rankings) + ((size_t)b * n + src) * K;
     float2* d = reinterpret_cast<float2*>(out) + ((size_t)b * R + j) * K;
     for (int k = lane; k < K; k += 32) d[k] = __ldg(s + k);
-    if (order_out != nullptr && lane == 0) order_out[(size_t)b * R + j] = (int32_t)(src - (uint32_t)b * (uint32_t)n);
+    if (order_out != nullptr && lane == 0) order_out[(size_t)b * R + j] = (int32_t)src;
   }
 }
+
+int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                   const int* len_dev, int len_max, size_t stride, int B, int* hist, cudaStream_t st);
+size_t seg_radix_sort_hist_bytes(int len_max, int B);
 
 }  // namespace pld
 
@@ -777,18 +774,12 @@ int pld_select_top(pld_ctx* ctx, const double* scores, const float* rankings, in
                    float* rankings_out, int32_t* order_out, void* stream) {
   PLD_REQUIRE(ctx && scores && rankings && rankings_out, "null argument");
   PLD_REQUIRE(B > 0 && B <= 65535 && n > 0 && K >= 1 && R >= 0 && R <= n, "bad shape");
-  PLD_REQUIRE((long long)B * n < (1ll << 32), "too many candidates");
+  PLD_REQUIRE((long long)B * n < (1ll << 31), "too many candidates");
   if (R == 0) return PLD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)B * n;
-  size_t tmp1 = 0, tmp2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, total, 0, 64, st);
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint16_t*)nullptr, (uint16_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, total, 0, 16, st);
-  const size_t tmp = tmp1 > tmp2 ? tmp1 : tmp2;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t need = al(total * 8) * 2 + al(total * 4) * 2 + al(total * 2) * 2 + al(tmp);
+  const size_t need = al(total * 8) * 2 + al(total * 4) * 2 + al(seg_radix_sort_hist_bytes(n, B));
   int rc = ctx->ensure_scratch(need);
   if (rc) return rc;
   char* base = (char*)ctx->d_scratch;
@@ -796,32 +787,17 @@ int pld_select_top(pld_ctx* ctx, const double* scores, const float* rankings, in
   uint64_t* k1 = (uint64_t*)base; base += al(total * 8);
   uint32_t* v0 = (uint32_t*)base; base += al(total * 4);
   uint32_t* v1 = (uint32_t*)base; base += al(total * 4);
-  uint16_t* i0 = (uint16_t*)base; base += al(total * 2);
-  uint16_t* i1 = (uint16_t*)base; base += al(total * 2);
-  void* dtmp = base;
-  int gx = (int)((total + 255) / 256);
-  if (gx > ctx->num_sms * 16) gx = ctx->num_sms * 16;
-  select_keys_kernel<<<gx, 256, 0, st>>>(scores, total, k0, v0);
-  PLD_CHECK_LAUNCH();
-  size_t t = tmp;
-  PLD_CUDA(cub::DeviceRadixSort::SortPairs(dtmp, t, k0, k1, v0, v1, total, 0, 64, st));
-  count_launch(8);
-  if (B > 1) {
-    select_image_kernel<<<gx, 256, 0, st>>>(v1, total, (uint32_t)n, i0);
-    PLD_CHECK_LAUNCH();
-    int bits = 1;
-    while ((1 << bits) < B) ++bits;
-    t = tmp;
-    PLD_CUDA(cub::DeviceRadixSort::SortPairs(dtmp, t, i0, i1, v1, v0, total, 0, bits, st));
-    count_launch(3);
-  } else {
-    PLD_CUDA(cudaMemcpyAsync(v0, v1, total * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  int gxr = (R + 7) / 8;
+  int* hist = (int*)base;
   const int cap = (ctx->num_sms * 8 + B - 1) / B;
+  int gx = (n + 255) / 256;
+  if (gx > cap) gx = cap;
+  select_keys_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(scores, n, k0, v0);
+  PLD_CHECK_LAUNCH();
+  rc = seg_radix_sort(ctx, k0, v0, k1, v1, nullptr, n, (size_t)n, B, hist, st);
+  if (rc) return rc;
+  int gxr = (R + 7) / 8;
   if (gxr > cap) gxr = cap;
-  dim3 grid((unsigned)gxr, (unsigned)B);
-  select_gather_kernel<<<grid, 256, 0, st>>>(v0, rankings, n, K, R, rankings_out, order_out);
+  select_gather_kernel<<<dim3((unsigned)gxr, (unsigned)B), 256, 0, st>>>(v0, rankings, n, K, R, rankings_out, order_out);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

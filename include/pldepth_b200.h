@@ -195,6 +195,20 @@ int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float
                    float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
                    float* per_list, float* grad, void* stream);
 
+/* Same step for the score-based strategies (Masked / Thresholded / InformationScore,
+ * sampling.py:157-169, 190-208, 218-239): n = int(R * factor) Philox candidate lists per image are drawn
+ * and scored (only the 8-byte ordered score is stored), a radix top-R selection + segmented radix sort
+ * orders the best R by score descending (ties: larger candidate index first), and the kept lists are
+ * REDRAWN from their Philox list ids inside the fused kernel that emits rankings / loss / gradient.
+ * Results equal pld_sample_lists_philox(n) -> pld_score_lists -> pld_select_top(R) -> pld_listmle_fwd_bwd.
+ * pred / loss / grad may be NULL (sampler only: rankings and order_out).  ranking_size 1..16.
+ *   -> order_out i32[B,R] (nullable): candidate index of every kept list */
+int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
+                          int Wm, int H, int W, int K, int n, int R, int strategy, double threshold,
+                          double equality_penalty, int promotion, uint64_t seed, uint64_t offset,
+                          int image_base, float scale, int32_t* n_valid, int32_t* order_out, float* rankings,
+                          float* loss, double* loss_sum, float* per_list, float* grad, void* stream);
+
 /* ---- evaluation metrics next to the training step ------------------------------
  * ordinal_error (pldepth/active_learning/metrics.py:60-70): pred, gt f32[N,HW]; idx0, idx1 i32[num] are
  * the fixed pixel pairs (np.random.seed(10); np.random.choice(HW, 2*num, replace=False), split in two);

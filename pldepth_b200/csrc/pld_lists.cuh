@@ -1,6 +1,7 @@
 // Per-list device building blocks: draws, ordering networks, ListMLE forward/backward.
 #pragma once
 #include "pld_common.cuh"
+#include "pld_score.cuh"
 
 namespace pld {
 
@@ -16,6 +17,12 @@ struct ListParams {
   const float2* table;         // [B, table_stride] (SRC_PHILOX_TAB), see prep_build_kernel
   size_t table_stride;
   float* rank_out;             // [B, n, K, 2] nullable
+  uint64_t* score_keys;        // [B, n] ordered scores (score mode of the small kernel)
+  ScoreCfg score_cfg;
+  // optional indirection: list l of image b redraws candidate list_map[b*map_stride + map_len[b]-1-l]
+  const uint32_t* list_map;
+  const int* map_len;
+  size_t map_stride;
   int32_t* sel_out;            // [B, n, K] nullable
   float* per_list;             // [B*n] nullable
   float* grad;                 // [B, HW] nullable

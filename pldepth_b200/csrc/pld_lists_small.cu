@@ -37,7 +37,7 @@ __device__ __forceinline__ void draw_philox(const ListParams& P, int b, int l, u
 #ifndef PLD_SMALL_MINBLOCKS
 #define PLD_SMALL_MINBLOCKS 1
 #endif
-template <int K, int SRC, bool LOSS>
+template <int K, int SRC, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
@@ -62,6 +62,16 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
   }
 
+  // Philox list id of the l-th list of this image: l itself, or the l-th best candidate of a
+  // previous scoring pass (list_map holds candidates in ascending score order; read backwards)
+  const uint32_t* __restrict__ lmap = nullptr;
+  int lmap_last = 0;
+  if (SRC == SRC_PHILOX_TAB && P.list_map != nullptr) {
+    lmap = P.list_map + (size_t)b * P.map_stride;
+    lmap_last = P.map_len[b] - 1;
+  }
+  auto philox_list = [&](int l) -> int { return lmap ? (int)__ldg(lmap + (lmap_last - l)) : l; };
+
   // software pipeline of the table path: the draws and table gathers of the NEXT list are issued
   // before the current list is ordered / scored, so their latency hides behind that work
   int pre_sel[K];
@@ -71,7 +81,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     tab = P.table + (size_t)b * P.table_stride;
     const int l0 = blockIdx.x * 256 + threadIdx.x;
     if (blockIdx.x * 256 < P.n) {
-      draw_philox<K>(P, b, l0 < P.n ? l0 : P.n - 1, M, thresh, pre_sel);
+      draw_philox<K>(P, b, philox_list(l0 < P.n ? l0 : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
       for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
     }
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           const int nbase = base + gridDim.x * 256;
           if (nbase < P.n) {
             const int ln = nbase + threadIdx.x;
-            draw_philox<K>(P, b, ln < P.n ? ln : P.n - 1, M, thresh, pre_sel);
+            draw_philox<K>(P, b, philox_list(ln < P.n ? ln : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
             for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
           }
@@ -197,6 +207,15 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
         for (int k = 0; k < K; ++k) {
           p[k] = (int)((uint32_t)key[k] & 0x7FFFFFu);
           lab[k] = ordered_to_float((uint32_t)(key[k] >> 32));
+        }
+        if (SCORE) {
+          // scoring pass of the score-based strategies: only the ordered score leaves the kernel; the
+          // kept lists are redrawn later from their Philox list id (cheaper than storing 8 B/point)
+          const double sc = (P.score_cfg.promotion == PLD_PROMOTION_NEP50)
+                                ? score_regs<float, K>(lab, P.score_cfg, b)
+                                : score_regs<double, K>(lab, P.score_cfg, b);
+          if (active) P.score_keys[list_id] = score_key(sc);
+          continue;
         }
         if (P.rank_out != nullptr) {
           float2* st = s_stage + wid * (32 * STRIDE);
@@ -272,6 +291,29 @@ static int launch_small_k(const ListParams& P, dim3 grid, cudaStream_t st) {
   return PLD_OK;
 }
 
+int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st) {
+  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  int gx = (P.n + 255) / 256;
+  if (gx > per_image_cap) gx = per_image_cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)P.B);
+  switch (P.K) {
+#define PLD_CASE(KK)                                                              \
+  case KK:                                                                        \
+    lists_small_kernel<KK, SRC_PHILOX_TAB, false, true><<<grid, 256, 0, st>>>(P); \
+    break;
+    PLD_CASE(1) PLD_CASE(2) PLD_CASE(3) PLD_CASE(4) PLD_CASE(5) PLD_CASE(6) PLD_CASE(7) PLD_CASE(8)
+    PLD_CASE(9) PLD_CASE(10) PLD_CASE(11) PLD_CASE(12) PLD_CASE(13) PLD_CASE(14) PLD_CASE(15)
+    PLD_CASE(16)
+#undef PLD_CASE
+    default:
+      set_error("lists_small_score: K=%d out of range", P.K);
+      return PLD_EINVAL;
+  }
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st) {
   const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
   int gx = (P.n + 255) / 256;
@@ -281,7 +323,8 @@ int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cud
   if (src == SRC_PHILOX) return loss ? launch_small_k<SRC_PHILOX, true>(P, grid, st) : launch_small_k<SRC_PHILOX, false>(P, grid, st);
   if (src == SRC_FED_SEL) return loss ? launch_small_k<SRC_FED_SEL, true>(P, grid, st) : launch_small_k<SRC_FED_SEL, false>(P, grid, st);
   if (src == SRC_FED_RANK) return launch_small_k<SRC_FED_RANK, true>(P, grid, st);
-  if (src == SRC_PHILOX_TAB) return launch_small_k<SRC_PHILOX_TAB, true>(P, grid, st);
+  if (src == SRC_PHILOX_TAB) return loss ? launch_small_k<SRC_PHILOX_TAB, true>(P, grid, st)
+                                         : launch_small_k<SRC_PHILOX_TAB, false>(P, grid, st);
   set_error("lists_small: bad source %d", src);
   return PLD_EINVAL;
 }

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "pld_common.cuh"
+#include "pld_score.cuh"
 
 namespace pld {
 
@@ -434,94 +435,14 @@ __global__ void __launch_bounds__(1024) gt_minmax_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// candidate scores (exactly NumPy's arithmetic; no FMA contraction)
+// candidate scores, staged API (pld_score.cuh holds the arithmetic)
 // ------------------------------------------------------------------------------------------
-template <typename T> struct Arith;
-template <> struct Arith<float> {
-  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-};
-template <> struct Arith<double> {
-  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-};
-
 struct ScoreParams {
-  const float* rankings;   // [B, n, K, 2]
-  const float* gt_minmax;  // [B, 2]
-  double* scores;          // [B, n]
-  int B, n, K, strategy;
-  double thr_hi, thr_lo, penalty;  // legacy (float64) thresholds
-  float thr_hi_f, thr_lo_f;        // nep50 (float32) thresholds
+  const float* rankings;  // [B, n, K, 2]
+  double* scores;         // [B, n]
+  int B, n, K;
+  ScoreCfg cfg;
 };
-
-template <typename T>
-__device__ __forceinline__ bool relation_equal(float g1, float g2, const ScoreParams& P) {
-  if (sizeof(T) == 4) {
-    const float r = __fdiv_rn(__fadd_rn(g1, 1e-10f), __fadd_rn(g2, 1e-10f));
-    return !(r >= P.thr_hi_f) && !(r <= P.thr_lo_f);
-  } else {
-    const double r = __ddiv_rn(__dadd_rn((double)g1, 1e-10), __dadd_rn((double)g2, 1e-10));
-    return !(r >= P.thr_hi) && !(r <= P.thr_lo);
-  }
-}
-
-// element k (0-based) of linspace(start, stop, K+1)[1:]  (numpy/_core/function_base.py)
-template <typename T>
-__device__ __forceinline__ T ladder(int k, int K, T start, T stop, T delta, T step) {
-  if (k == K - 1) return stop;
-  const T i = (T)(k + 1);
-  if (step == (T)0) return Arith<T>::add(Arith<T>::mul(Arith<T>::div(i, (T)K), delta), start);
-  return Arith<T>::add(Arith<T>::mul(i, step), start);
-}
-
-template <typename T>
-struct ChiTerm {
-  const float2* r;
-  int K;
-  T start, stop, delta, step;
-  __device__ __forceinline__ T operator()(int k) const {
-    const T e = ladder<T>(k, K, start, stop, delta, step);
-    const T d = Arith<T>::sub((T)__ldg(&r[k].y), e);
-    return Arith<T>::div(Arith<T>::mul(d, d), e);
-  }
-};
-
-// NumPy pairwise summation (umath loops_utils.h pairwise_sum): n < 8 sequential; n <= 128 eight
-// running accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the tail; larger n
-// split at n/2 rounded down to a multiple of 8.
-template <typename T, typename F>
-__device__ T np_pairwise_sum(const F& f, int lo, int n) {
-  using A = Arith<T>;
-  if (n < 8) {
-    T res = (T)0;
-    for (int i = 0; i < n; ++i) res = A::add(res, f(lo + i));
-    return res;
-  }
-  if (n <= 128) {
-    T r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = f(lo + j);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], f(lo + i + j));
-    }
-    T res = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])),
-                   A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
-    for (; i < n; ++i) res = A::add(res, f(lo + i));
-    return res;
-  }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  const T a = np_pairwise_sum<T, F>(f, lo, n2);
-  const T b = np_pairwise_sum<T, F>(f, lo + n2, n - n2);
-  return A::add(a, b);
-}
 
 template <typename T>
 __global__ void __launch_bounds__(256) score_kernel(const ScoreParams P) {
@@ -529,41 +450,8 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams P) {
   for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < P.n; l += gridDim.x * blockDim.x) {
     const size_t list_id = (size_t)b * P.n + l;
     const float2* r = reinterpret_cast<const float2*>(P.rankings) + list_id * P.K;
-    double score;
-    if (P.strategy == PLD_STRATEGY_INFORMATION) {
-      T start, stop;
-      if (sizeof(T) == 4) {
-        start = (T)__fadd_rn(P.gt_minmax[b * 2], 0.001f);
-      } else {
-        start = (T)__dadd_rn((double)P.gt_minmax[b * 2], 0.001);
-      }
-      stop = (T)P.gt_minmax[b * 2 + 1];
-      const T delta = Arith<T>::sub(stop, start);
-      const T step = Arith<T>::div(delta, (T)P.K);
-      ChiTerm<T> term{r, P.K, start, stop, delta, step};
-      const T sum = np_pairwise_sum<T, ChiTerm<T>>(term, 0, P.K);
-      score = (double)(-sum);
-      float gprev = __ldg(&r[0].y);
-      for (int j = 0; j + 1 < P.K; ++j) {
-        const float gn = __ldg(&r[j + 1].y);
-        if (relation_equal<T>(gprev, gn, P)) score = __dadd_rn(score, P.penalty);
-        gprev = gn;
-      }
-    } else {
-      T acc = (T)0;
-      const T pen = (T)P.penalty;
-      float gprev = __ldg(&r[0].y);
-      for (int j = 0; j + 1 < P.K; ++j) {
-        const float gn = __ldg(&r[j + 1].y);
-        const float diff = fabsf(__fsub_rn(gprev, gn));
-        if (P.strategy == PLD_STRATEGY_THRESHOLDED && relation_equal<T>(gprev, gn, P))
-          acc = Arith<T>::add(acc, pen);
-        acc = Arith<T>::add(acc, (T)diff);
-        gprev = gn;
-      }
-      score = (double)acc;
-    }
-    P.scores[list_id] = score;
+    auto g = [r](int k) { return __ldg(&r[k].y); };
+    P.scores[list_id] = score_list<T>(g, P.K, P.cfg, b);
   }
 }
 
@@ -575,9 +463,7 @@ __global__ void __launch_bounds__(256) select_keys_kernel(const double* __restri
                                                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const size_t off = (size_t)blockIdx.y * n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    double s = scores[off + i];
-    if (s == 0.0) s = 0.0;  // -0.0 == +0.0 for argsort
-    keys[off + i] = double_to_ordered(s);
+    keys[off + i] = score_key(scores[off + i]);
     vals[off + i] = (uint32_t)i;
   }
 }
@@ -753,13 +639,8 @@ int pld_score_lists(pld_ctx* ctx, const float* rankings, const float* gt_minmax,
   PLD_REQUIRE(strategy != PLD_STRATEGY_INFORMATION || gt_minmax != nullptr, "gt_minmax required");
   PLD_REQUIRE(promotion == PLD_PROMOTION_NEP50 || promotion == PLD_PROMOTION_LEGACY, "bad promotion");
   ScoreParams P;
-  P.rankings = rankings; P.gt_minmax = gt_minmax; P.scores = scores;
-  P.B = B; P.n = n; P.K = K; P.strategy = strategy;
-  P.thr_hi = 1.0 + threshold;            // depth_utils.py:16
-  P.thr_lo = 1.0 / (1.0 + threshold);    // depth_utils.py:18
-  P.thr_hi_f = (float)P.thr_hi;
-  P.thr_lo_f = (float)P.thr_lo;
-  P.penalty = equality_penalty;
+  P.rankings = rankings; P.scores = scores; P.B = B; P.n = n; P.K = K;
+  P.cfg = make_score_cfg(gt_minmax, strategy, threshold, equality_penalty, promotion);
   int gx = (n + 255) / 256;
   const int cap = (ctx->num_sms * 8 + B - 1) / B;
   if (gx > cap) gx = cap;

@@ -1,0 +1,199 @@
+// Candidate scores of the score-based strategies, reproducing NumPy's arithmetic operation for
+// operation (no FMA contraction): sampling.py:161-167 (masked), 194-205 (thresholded), 219-237
+// (information), get_depth_relation depth_utils.py:5-21.  Shared by the staged score kernel
+// (runtime K, lists read from memory) and the fused list kernel (K <= 16, list in registers).
+#pragma once
+#include "pld_common.cuh"
+
+namespace pld {
+
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Arith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+struct ScoreCfg {
+  const float* gt_minmax;          // [B, 2] (information)
+  int strategy;                    // PLD_STRATEGY_*
+  int promotion;                   // PLD_PROMOTION_*
+  double thr_hi, thr_lo, penalty;  // legacy (float64) thresholds
+  float thr_hi_f, thr_lo_f;        // nep50 (float32) thresholds
+};
+
+inline ScoreCfg make_score_cfg(const float* gt_minmax, int strategy, double threshold, double penalty, int promotion) {
+  ScoreCfg c;
+  c.gt_minmax = gt_minmax;
+  c.strategy = strategy;
+  c.promotion = promotion;
+  c.thr_hi = 1.0 + threshold;          // depth_utils.py:16
+  c.thr_lo = 1.0 / (1.0 + threshold);  // depth_utils.py:18
+  c.thr_hi_f = (float)c.thr_hi;
+  c.thr_lo_f = (float)c.thr_lo;
+  c.penalty = penalty;
+  return c;
+}
+
+template <typename T>
+__device__ __forceinline__ bool relation_equal(float g1, float g2, const ScoreCfg& P) {
+  if (sizeof(T) == 4) {
+    const float r = __fdiv_rn(__fadd_rn(g1, 1e-10f), __fadd_rn(g2, 1e-10f));
+    return !(r >= P.thr_hi_f) && !(r <= P.thr_lo_f);
+  } else {
+    const double r = __ddiv_rn(__dadd_rn((double)g1, 1e-10), __dadd_rn((double)g2, 1e-10));
+    return !(r >= P.thr_hi) && !(r <= P.thr_lo);
+  }
+}
+
+// element k (0-based) of linspace(start, stop, K+1)[1:]  (numpy/_core/function_base.py)
+template <typename T>
+__device__ __forceinline__ T ladder(int k, int K, T start, T stop, T delta, T step) {
+  if (k == K - 1) return stop;
+  const T i = (T)(k + 1);
+  if (step == (T)0) return Arith<T>::add(Arith<T>::mul(Arith<T>::div(i, (T)K), delta), start);
+  return Arith<T>::add(Arith<T>::mul(i, step), start);
+}
+
+template <typename T>
+__device__ __forceinline__ void ladder_setup(const ScoreCfg& C, int b, int K, T& start, T& stop, T& delta, T& step) {
+  if (sizeof(T) == 4) start = (T)__fadd_rn(C.gt_minmax[b * 2], 0.001f);      // sampling.py:223
+  else start = (T)__dadd_rn((double)C.gt_minmax[b * 2], 0.001);
+  stop = (T)C.gt_minmax[b * 2 + 1];
+  delta = Arith<T>::sub(stop, start);
+  step = Arith<T>::div(delta, (T)K);
+}
+
+// NumPy pairwise summation (umath loops_utils.h pairwise_sum): n < 8 sequential; n <= 128 eight
+// running accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the tail; larger n
+// split at n/2 rounded down to a multiple of 8.
+template <typename T, typename F>
+__device__ T np_pairwise_sum(const F& f, int lo, int n) {
+  using A = Arith<T>;
+  if (n < 8) {
+    T res = (T)0;
+    for (int i = 0; i < n; ++i) res = A::add(res, f(lo + i));
+    return res;
+  }
+  if (n <= 128) {
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f(lo + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], f(lo + i + j));
+    }
+    T res = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])),
+                   A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
+    for (; i < n; ++i) res = A::add(res, f(lo + i));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const T a = np_pairwise_sum<T, F>(f, lo, n2);
+  const T b = np_pairwise_sum<T, F>(f, lo + n2, n - n2);
+  return A::add(a, b);
+}
+
+// Score of a list whose depths are read through `g(k)` (runtime K).
+template <typename T, typename G>
+__device__ __forceinline__ double score_list(const G& g, int K, const ScoreCfg& C, int b) {
+  double score;
+  if (C.strategy == PLD_STRATEGY_INFORMATION) {
+    T start, stop, delta, step;
+    ladder_setup<T>(C, b, K, start, stop, delta, step);
+    auto chi = [&](int k) {
+      const T e = ladder<T>(k, K, start, stop, delta, step);
+      const T d = Arith<T>::sub((T)g(k), e);
+      return Arith<T>::div(Arith<T>::mul(d, d), e);
+    };
+    const T sum = np_pairwise_sum<T>(chi, 0, K);
+    score = (double)(-sum);
+    float gprev = g(0);
+    for (int j = 0; j + 1 < K; ++j) {
+      const float gn = g(j + 1);
+      if (relation_equal<T>(gprev, gn, C)) score = __dadd_rn(score, C.penalty);
+      gprev = gn;
+    }
+  } else {
+    T acc = (T)0;
+    const T pen = (T)C.penalty;
+    float gprev = g(0);
+    for (int j = 0; j + 1 < K; ++j) {
+      const float gn = g(j + 1);
+      const float diff = fabsf(__fsub_rn(gprev, gn));
+      if (C.strategy == PLD_STRATEGY_THRESHOLDED && relation_equal<T>(gprev, gn, C)) acc = Arith<T>::add(acc, pen);
+      acc = Arith<T>::add(acc, (T)diff);
+      gprev = gn;
+    }
+    score = (double)acc;
+  }
+  return score;
+}
+
+// Same arithmetic for a list held in registers (compile-time K <= 16, fully unrolled).
+template <typename T, int K>
+__device__ __forceinline__ double score_regs(const float (&g)[K], const ScoreCfg& C, int b) {
+  static_assert(K <= 16, "register scoring supports K <= 16");
+  using A = Arith<T>;
+  double score;
+  if (C.strategy == PLD_STRATEGY_INFORMATION) {
+    T start, stop, delta, step;
+    ladder_setup<T>(C, b, K, start, stop, delta, step);
+    T chi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const T e = ladder<T>(k, K, start, stop, delta, step);
+      const T d = A::sub((T)g[k], e);
+      chi[k] = A::div(A::mul(d, d), e);
+    }
+    T sum;
+    if constexpr (K < 8) {
+      sum = (T)0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) sum = A::add(sum, chi[k]);
+    } else {
+      T r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = chi[j];
+      if constexpr (K == 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = A::add(r[j], chi[8 + j]);
+      }
+      sum = A::add(A::add(A::add(r[0], r[1]), A::add(r[2], r[3])), A::add(A::add(r[4], r[5]), A::add(r[6], r[7])));
+#pragma unroll
+      for (int k = K - (K % 8); k < K; ++k) sum = A::add(sum, chi[k]);
+    }
+    score = (double)(-sum);
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j)
+      if (relation_equal<T>(g[j], g[j + 1], C)) score = __dadd_rn(score, C.penalty);
+  } else {
+    T acc = (T)0;
+    const T pen = (T)C.penalty;
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j) {
+      const float diff = fabsf(__fsub_rn(g[j], g[j + 1]));
+      if (C.strategy == PLD_STRATEGY_THRESHOLDED && relation_equal<T>(g[j], g[j + 1], C)) acc = A::add(acc, pen);
+      acc = A::add(acc, (T)diff);
+    }
+    score = (double)acc;
+  }
+  return score;
+}
+
+// order-preserving u64 image of a score (== what np.argsort compares; -0.0 == +0.0)
+__device__ __forceinline__ uint64_t score_key(double s) {
+  if (s == 0.0) s = 0.0;
+  return double_to_ordered(s);
+}
+
+}  // namespace pld

@@ -16,6 +16,10 @@
 namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
+int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
+int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                   const int* len_dev, int len_max, size_t stride, int B, int* hist, cudaStream_t st);
+size_t seg_radix_sort_hist_bytes(int len_max, int B);
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_ITEMS = 16;
@@ -138,6 +142,179 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   if (chunk == 0 && threadIdx.x == 0) n_valid[b] = total;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// radix top-R selection on the ordered scores: three 12-bit MSB-first histogram passes locate, per
+// image, the 36-bit key prefix T such that  #{prefix > T} < R <= #{prefix >= T};  every candidate
+// with prefix >= T survives (R' >= R of them, the surplus being the ties of the boundary bucket),
+// is compacted in candidate order and fully sorted afterwards.
+// ------------------------------------------------------------------------------------------
+constexpr int SEL_BINS = 4096;
+
+__global__ void __launch_bounds__(256) gt_minmax_step_kernel(const float* __restrict__ gt, int HW, float* __restrict__ out) {
+  const float* g = gt + (size_t)blockIdx.x * HW;
+  float mn = 3.402823466e38f, mx = -3.402823466e38f;
+  for (int i = threadIdx.x; i < HW; i += 256) {
+    const float v = __ldg(g + i);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[8], smx[8];
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    out[blockIdx.x * 2 + 0] = mn;
+    out[blockIdx.x * 2 + 1] = mx;
+  }
+}
+
+__global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < B * SEL_BINS; i += gridDim.x * 256) hist[i] = 0u;
+  if (blockIdx.x == 0 && (int)threadIdx.x < B) { prefix[threadIdx.x] = 0ull; remaining[threadIdx.x] = R; }
+  if (blockIdx.x == 0)
+    for (int i = 256 + threadIdx.x; i < B; i += 256) { prefix[i] = 0ull; remaining[i] = R; }
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restrict__ keys, int n, int pass,
+                                                       const uint64_t* __restrict__ prefix, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_h[SEL_BINS];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < SEL_BINS; i += 256) s_h[i] = 0u;
+  __syncthreads();
+  const uint64_t* k = keys + (size_t)b * n;
+  const int shift = 64 - 12 * (pass + 1);
+  const uint64_t pre = prefix[b];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const uint64_t key = k[i];
+    const bool match = (pass == 0) || ((key >> (64 - 12 * pass)) == pre);
+    if (match) atomicAdd(&s_h[(int)((key >> shift) & 0xFFF)], 1u);
+  }
+  __syncthreads();
+  unsigned int* h = hist + (size_t)b * SEL_BINS;
+  for (int i = threadIdx.x; i < SEL_BINS; i += 256)
+    if (s_h[i]) atomicAdd(h + i, s_h[i]);
+}
+
+// one CTA per image: largest bin t with  sum_{bin >= t} hist >= remaining
+__global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
+                                                       int* __restrict__ remaining) {
+  __shared__ unsigned int s_sum[256];
+  const int b = blockIdx.x;
+  unsigned int* h = hist + (size_t)b * SEL_BINS;
+  // thread t owns the 16 bins [4096 - 16(t+1), 4096 - 16t): thread 0 holds the top bins
+  const int hi = SEL_BINS - 16 * threadIdx.x;
+  unsigned int loc[16], tot = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { loc[i] = h[hi - 1 - i]; tot += loc[i]; }
+  s_sum[threadIdx.x] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int need = (unsigned int)remaining[b];
+    unsigned int above = 0;
+    int t = 0;
+    while (t < 255 && above + s_sum[t] < need) { above += s_sum[t]; ++t; }
+    s_sum[0] = (unsigned int)t;        // owner thread
+    s_sum[1] = above;                  // candidates in bins above the owner's range
+  }
+  __syncthreads();
+  const int owner = (int)s_sum[0];
+  const unsigned int above0 = s_sum[1];
+  __syncthreads();
+  if ((int)threadIdx.x == owner) {
+    const unsigned int need = (unsigned int)remaining[b];
+    unsigned int above = above0;
+    int i = 0;
+    while (i < 15 && above + loc[i] < need) { above += loc[i]; ++i; }
+    const int bin = hi - 1 - i;
+    prefix[b] = (prefix[b] << 12) | (uint64_t)bin;
+    remaining[b] = (int)(need - above);   // still to take from inside this bin
+  }
+  // clear the histogram for the next pass
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[hi - 1 - i] = 0u;
+}
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 16;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS) sel_count_kernel(const uint64_t* __restrict__ keys, int n, int ntiles,
+                                                              const uint64_t* __restrict__ prefix, int* __restrict__ counts) {
+  __shared__ int s_warp[SC_THREADS / 32];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const uint64_t* k = keys + (size_t)b * n;
+  const uint64_t T = prefix[b];
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    const int idx = tile * SC_TILE + i * SC_THREADS + threadIdx.x;
+    if (idx < n && (k[idx] >> 28) >= T) ++c;
+  }
+  const int tot = block_sum_int(c, s_warp);
+  if (threadIdx.x == 0) counts[b * ntiles + tile] = tot;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t* __restrict__ keys, int n, int ntiles,
+                                                                const uint64_t* __restrict__ prefix,
+                                                                const int* __restrict__ counts, uint64_t* __restrict__ keys_s,
+                                                                uint32_t* __restrict__ vals_s, int* __restrict__ n_surv) {
+  __shared__ int s_warp[SC_THREADS / 32];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  int pre = 0, all = 0;
+  for (int i = threadIdx.x; i < ntiles; i += SC_THREADS) {
+    const int c = counts[b * ntiles + i];
+    all += c;
+    if (i < tile) pre += c;
+  }
+  const int total = block_sum_int(all, s_warp);
+  const int prefix_cnt = block_sum_int(pre, s_warp);
+  if (tile == 0 && threadIdx.x == 0) n_surv[b] = total;
+  const uint64_t* k = keys + (size_t)b * n;
+  const uint64_t T = prefix[b];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wbase = tile * SC_TILE + wid * (SC_ITEMS * 32);   // each warp owns 512 consecutive candidates
+  uint32_t bal[SC_ITEMS];
+  uint64_t kv[SC_ITEMS];
+  int wcount = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    kv[i] = (idx < n) ? k[idx] : 0ull;
+    bal[i] = __ballot_sync(0xffffffffu, idx < n && (kv[i] >> 28) >= T);
+    wcount += __popc(bal[i]);
+  }
+  __syncthreads();
+  if (lane == 0) s_warp[wid] = wcount;
+  __syncthreads();
+  int rank = prefix_cnt;
+  for (int i = 0; i < wid; ++i) rank += s_warp[i];
+  const uint32_t lt = (1u << lane) - 1u;
+  const size_t off = (size_t)b * n;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    if ((bal[i] >> lane) & 1u) {
+      const int pos = rank + __popc(bal[i] & lt);
+      keys_s[off + pos] = kv[i];
+      vals_s[off + pos] = (uint32_t)(wbase + i * 32 + lane);
+    }
+    rank += __popc(bal[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restrict__ vals_s, const int* __restrict__ n_surv,
+                                                        int n, int R, int32_t* __restrict__ order_out) {
+  const int b = blockIdx.y;
+  const int last = n_surv[b] - 1;
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < R; j += gridDim.x * 256)
+    order_out[(size_t)b * R + j] = (int32_t)vals_s[(size_t)b * n + (last - j)];
+}
+
 }  // namespace pld
 
 using namespace pld;
@@ -207,6 +384,150 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   }
   ctx->time_begin(st);
   rc = launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
+  ctx->time_end(st);
+  if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
+  return rc;
+}
+
+extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
+                                     int Wm, int H, int W, int K, int n, int R, int strategy, double threshold,
+                                     double equality_penalty, int promotion, uint64_t seed, uint64_t offset,
+                                     int image_base, float scale, int32_t* n_valid, int32_t* order_out, float* rankings,
+                                     float* loss, double* loss_sum, float* per_list, float* grad, void* stream) {
+  PLD_REQUIRE(ctx && mask && gt, "null argument");
+  PLD_REQUIRE(pred != nullptr || (loss == nullptr && grad == nullptr && per_list == nullptr), "pred is required for the loss");
+  PLD_REQUIRE(rankings != nullptr || loss != nullptr, "no output requested");
+  PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
+  PLD_REQUIRE((long long)H * W <= PLD_MAX_PIXELS && (long long)Hm * Wm <= PLD_MAX_PIXELS, "map too large");
+  PLD_REQUIRE(K >= 1 && K <= 16, "pld_fused_step_scored supports ranking_size 1..16 (use the staged calls above that)");
+  PLD_REQUIRE(n >= 1 && R >= 1 && R <= n && (long long)B * n < (1ll << 31), "need 1 <= R <= n candidates");
+  PLD_REQUIRE(strategy >= PLD_STRATEGY_MASKED && strategy <= PLD_STRATEGY_INFORMATION, "bad strategy");
+  PLD_REQUIRE(promotion == PLD_PROMOTION_NEP50 || promotion == PLD_PROMOTION_LEGACY, "bad promotion");
+  PLD_REQUIRE((offset >> 48) == 0, "offset must fit in 48 bits");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W, Nm = Hm * Wm;
+  const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
+  const int ntiles = (n + SC_TILE - 1) / SC_TILE;
+  const size_t tstride = (size_t)(HW > Nm ? HW : Nm);
+  const size_t total = (size_t)B * n;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += al(bytes); return o; };
+  const size_t o_counts = take(sizeof(int) * (size_t)B * nchunks);
+  const size_t o_nv = take(sizeof(int32_t) * B);
+  const size_t o_mm = take(sizeof(float) * 2 * B);
+  const size_t o_prefix = take(sizeof(uint64_t) * B);
+  const size_t o_rem = take(sizeof(int) * B);
+  const size_t o_nsurv = take(sizeof(int) * B);
+  const size_t o_shist = take(sizeof(unsigned int) * (size_t)B * SEL_BINS);
+  const size_t o_tcnt = take(sizeof(int) * (size_t)B * ntiles);
+  const size_t o_keys = take(sizeof(uint64_t) * total);
+  const size_t o_k0 = take(sizeof(uint64_t) * total);
+  const size_t o_k1 = take(sizeof(uint64_t) * total);
+  const size_t o_v0 = take(sizeof(uint32_t) * total);
+  const size_t o_v1 = take(sizeof(uint32_t) * total);
+  const size_t o_rhist = take(seg_radix_sort_hist_bytes(n, B));
+  const size_t o_tab = take(sizeof(float2) * (size_t)B * tstride);
+  int rc = ctx->ensure_scratch(off);
+  if (rc) return rc;
+  char* sb = (char*)ctx->d_scratch;
+  int* counts = (int*)(sb + o_counts);
+  int32_t* nv = n_valid ? n_valid : (int32_t*)(sb + o_nv);
+  float* minmax = (float*)(sb + o_mm);
+  uint64_t* prefix = (uint64_t*)(sb + o_prefix);
+  int* remaining = (int*)(sb + o_rem);
+  int* n_surv = (int*)(sb + o_nsurv);
+  unsigned int* shist = (unsigned int*)(sb + o_shist);
+  int* tcnt = (int*)(sb + o_tcnt);
+  uint64_t* keys = (uint64_t*)(sb + o_keys);
+  uint64_t* k0 = (uint64_t*)(sb + o_k0);
+  uint64_t* k1 = (uint64_t*)(sb + o_k1);
+  uint32_t* v0 = (uint32_t*)(sb + o_v0);
+  uint32_t* v1 = (uint32_t*)(sb + o_v1);
+  int* rhist = (int*)(sb + o_rhist);
+  float2* table = (float2*)(sb + o_tab);
+  const int per_image_cap = (ctx->num_sms * 8 + B - 1) / B;
+  rc = ctx->ensure_partials(per_image_cap * B + B);
+  if (rc) return rc;
+
+  // 1. valid pixels + zeroed grad + lookup tables (as pld_fused_step)
+  dim3 pgrid((unsigned)nchunks, (unsigned)B);
+  const size_t gtotal = (size_t)B * HW;
+  float4* g4 = nullptr;
+  size_t n4 = 0;
+  int tail = 0;
+  if (grad != nullptr) {
+    PLD_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
+    g4 = reinterpret_cast<float4*>(grad);
+    n4 = gtotal / 4;
+    tail = (int)(gtotal - n4 * 4);
+  }
+  prep_count_kernel<<<pgrid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
+  PLD_CHECK_LAUNCH();
+  const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
+  const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
+  prep_build_kernel<<<pgrid, PC_THREADS, 0, st>>>(mask, gt, pred ? pred : gt, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks,
+                                                 counts, table, tstride, nv);
+  PLD_CHECK_LAUNCH();
+  if (strategy == PLD_STRATEGY_INFORMATION) {
+    gt_minmax_step_kernel<<<B, 256, 0, st>>>(gt, HW, minmax);
+    PLD_CHECK_LAUNCH();
+  }
+
+  // 2. scoring pass over the n candidates of every image: ordered scores only
+  ListParams P = {};
+  P.gt = gt; P.pred = pred ? pred : gt; P.n_valid = nv; P.table = table; P.table_stride = tstride;
+  P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
+  P.B = B; P.HW = HW; P.n = n; P.K = K; P.scale = scale;
+  P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+  P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
+  P.image_base = image_base;
+  P.score_keys = keys;
+  P.score_cfg = make_score_cfg(minmax, strategy, threshold, equality_penalty, promotion);
+  rc = launch_lists_small_score(P, ctx->num_sms, st);
+  if (rc) return rc;
+
+  // 3. radix top-R selection -> survivors in candidate order
+  int gsel = (n + 255) / 256;
+  if (gsel > per_image_cap) gsel = per_image_cap;
+  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B);
+  PLD_CHECK_LAUNCH();
+  for (int pass = 0; pass < 3; ++pass) {
+    sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
+    PLD_CHECK_LAUNCH();
+    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, remaining);
+    PLD_CHECK_LAUNCH();
+  }
+  dim3 tgrid((unsigned)ntiles, (unsigned)B);
+  sel_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt);
+  PLD_CHECK_LAUNCH();
+  sel_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt, k0, v0, n_surv);
+  PLD_CHECK_LAUNCH();
+
+  // 4. full order of the survivors (ascending, stable); the best R are the tail read backwards
+  rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, st);
+  if (rc) return rc;
+  if (order_out != nullptr) {
+    int go = (R + 255) / 256;
+    if (go > per_image_cap) go = per_image_cap;
+    sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, n_surv, n, R, order_out);
+    PLD_CHECK_LAUNCH();
+  }
+
+  // 5. redraw the kept lists from their Philox ids: emit rankings, loss and gradient
+  P.score_keys = nullptr;
+  P.n = R;
+  P.list_map = v0; P.map_len = n_surv; P.map_stride = (size_t)n;
+  P.rank_out = rankings; P.per_list = per_list; P.grad = grad; P.loss = loss; P.loss_sum = loss_sum;
+  const bool do_loss = loss != nullptr;
+  if (do_loss && grad != nullptr && ctx->deterministic) {
+    rc = ctx->ensure_acc(gtotal);
+    if (rc) return rc;
+    P.acc = ctx->d_acc;
+    PLD_CUDA(cudaMemsetAsync(P.acc, 0, sizeof(long long) * gtotal, st));
+  }
+  ctx->time_begin(st);
+  rc = launch_lists_small(P, SRC_PHILOX_TAB, do_loss, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   return rc;

@@ -254,6 +254,41 @@ def fused_step(mask, gt, pred, K, n, seed, offset=0, image_base=0, scale=None, w
     return loss, loss_sum, grad, rankings, per_list, n_valid
 
 
+def fused_step_scored(mask, gt, pred, K, n, R, strategy, threshold=0.03, equality_penalty=-1000, promotion="nep50",
+                      seed=0, offset=0, image_base=0, scale=None, want_rankings=True, want_grad=True, want_order=False,
+                      want_per_list=False):
+    """pld_fused_step_scored: draw n candidates/image, score, keep the best R, (optionally) loss + gradient.
+    ``pred`` may be None (sampler only).  Returns dict(loss, loss_sum, grad, rankings, order, per_list, n_valid)."""
+    mask = as_cuda(mask, torch.float32, "mask")
+    gt3 = as_cuda(gt, torch.float32, "gt")
+    if gt3.dim() == 4:
+        gt3 = gt3[..., 0].contiguous()
+    B, H, W = gt3.shape
+    Hm, Wm = mask.shape[1], mask.shape[2]
+    dev = gt3.device
+    do_loss = pred is not None
+    if do_loss:
+        pred = as_cuda(pred, torch.float32, "pred")
+    if scale is None:
+        scale = 1.0 / float(B * R)
+    ctx = _ctx(gt3)
+    with torch.cuda.device(dev):
+        loss = torch.empty(1, dtype=torch.float32, device=dev) if do_loss else None
+        loss_sum = torch.empty(1, dtype=torch.float64, device=dev) if do_loss else None
+        n_valid = torch.empty(B, dtype=torch.int32, device=dev)
+        rankings = torch.empty((B, R, K, 2), dtype=torch.float32, device=dev) if (want_rankings or not do_loss) else None
+        grad = torch.empty_like(pred) if (do_loss and want_grad) else None
+        order = torch.empty((B, R), dtype=torch.int32, device=dev) if want_order else None
+        per_list = torch.empty(B * R, dtype=torch.float32, device=dev) if (do_loss and want_per_list) else None
+        check(ctx.lib.pld_fused_step_scored(ctx.handle, _p(mask), _p(gt3), _p(pred), B, Hm, Wm, H, W, int(K), int(n),
+                                            int(R), _lib.STRATEGY[strategy], float(threshold), float(equality_penalty),
+                                            _lib.PROMOTION[promotion], int(seed), int(offset), int(image_base),
+                                            float(scale), _p(n_valid), _p(order), _p(rankings), _p(loss), _p(loss_sum),
+                                            _p(per_list), _p(grad), _stream(dev)))
+    return dict(loss=loss, loss_sum=loss_sum, grad=grad, rankings=rankings, order=order, per_list=per_list,
+                n_valid=n_valid)
+
+
 def check_status(device=None):
     """Synchronise the current stream of ``device`` and raise the Python exception the
     reference would have raised for bad data (empty mask, index out of range)."""

@@ -175,6 +175,21 @@ class PurelyMaskedRandomSamplingStrategy(RandomSamplingStrategy):
         """Whole-batch device sampling: returns rankings [B, n_out, K, 2] (device)."""
         f = self._default_factor if batch_size_factor is None else batch_size_factor
         n = int(batch_size * f)
+        K = int(self._num_points_per_sample)
+        if self.rng == "philox" and self._strategy != "purely" and K <= 16 and n >= 1:
+            # fast path: score-only pass, radix top-R, kept lists redrawn from their Philox ids
+            gt3 = ops.as_cuda(gt, torch.float32, "gt")
+            if gt3.dim() == 4 and gt3.shape[-1] == 1:
+                gt3 = gt3[..., 0]
+            if image_shape is not None and (int(image_shape[0]) != gt3.shape[1] or int(image_shape[1]) != gt3.shape[2]):
+                raise ValueError("gt and image must have the same height/width")
+            with self._lock:
+                off = self._calls
+                self._calls += 1
+            thr, pen = getattr(self, "threshold", 0.03), getattr(self, "equality_penalty", -1000)
+            out = ops.fused_step_scored(mask, gt3.contiguous(), None, K, n, min(batch_size, n), self._strategy, thr, pen,
+                                        self.promotion, self.seed, off, image_base)
+            return out["rankings"]
         cand = self.draw_candidates(gt, mask, n, image_shape, image_base)
         scores = self.score_candidates(cand, gt)
         if scores is None:

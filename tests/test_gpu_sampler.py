@@ -245,3 +245,67 @@ def test_provider_mirror_per_image_and_batched(cuda_device):
     assert tuple(img_b.shape) == (3, H, W, 3) and tuple(y_true.shape) == (3, 64, 5, 2)
     d = y_true[..., 1]
     assert bool((d[:, :, :-1] >= d[:, :, 1:]).all())
+
+
+@pytest.mark.parametrize("strategy", ["masked", "thresholded", "information"])
+@pytest.mark.parametrize("promotion", ["nep50", "legacy"])
+@pytest.mark.parametrize("K,geometry", [(2, "full"), (5, "holes"), (5, "ties"), (8, "scaled"), (9, "full"), (16, "holes")])
+def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K, geometry):
+    """pld_fused_step_scored (score-only pass + radix top-R + redraw) returns the same kept candidates, in
+    the same order, with the same rankings as the staged sample -> score -> select_top pipeline (which the
+    tests above pin to the oracle), and its loss / gradient match the oracle."""
+    from oracle import listmle_oracle as lo
+    from pldepth_b200 import ops
+    from tests.golden.make_golden import near_threshold_gt
+    B, H, W, n, R = 3, 40, 36, 700, 333
+    Hm, Wm = (20, 12) if geometry == "scaled" else (H, W)
+    rs = np.random.RandomState(K)
+    if geometry == "ties":       # few distinct depths: massive score ties -> tie rule and a big boundary bucket
+        gt = (rs.randint(0, 6, size=(B, H, W)) / 8 + 0.1).astype(np.float32)
+    else:
+        gt = np.stack([near_threshold_gt(H, W, 11 * K + b) for b in range(B)])
+    mask = np.ones((B, Hm, Wm), np.float32)
+    if geometry in ("holes", "scaled"):
+        mask = (rs.rand(B, Hm, Wm) > 0.3).astype(np.float32)
+        if geometry == "holes":
+            mask[1] = 1.0
+    pred = rs.randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    out = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, promotion, seed=4, offset=2,
+                                image_base=1, want_order=True, want_per_list=True)
+    vf, nv = ops.mask_compact(mask_d, H, W)
+    cand, _ = ops.sample_lists_philox(gt_d, vf, nv, K, n, 4, 2, 1)
+    mm = ops.gt_minmax(gt_d) if strategy == "information" else None
+    scores = ops.score_lists(cand, strategy, 0.03, -1000, promotion, mm)
+    top, order = ops.select_top(scores, cand, R, want_order=True)
+    ops.check_status(cuda_device)
+    assert torch.equal(out["order"], order)
+    assert torch.equal(out["rankings"], top)
+    want_loss, want_grad, want_pl = lo.hourglass_nll(top.cpu().numpy(), pred, B, K)
+    assert abs(out["loss"].item() - want_loss) <= 1e-5 * abs(want_loss)
+    err = np.abs(out["grad"].cpu().numpy() - want_grad).max() / np.abs(want_grad).max()
+    assert err <= 1e-5
+    # sampler-only variant (no pred): same rankings
+    out2 = ops.fused_step_scored(mask_d, gt_d, None, K, n, R, strategy, 0.03, -1000, promotion, seed=4, offset=2,
+                                 image_base=1)
+    assert torch.equal(out2["rankings"], top) and out2["loss"] is None
+
+
+def test_strategy_classes_use_fast_path_consistently(cuda_device):
+    """sample_batch in Philox mode (fast scored path) == draw_candidates + score + select (staged)."""
+    from pldepth_b200 import ops, sampling
+    from pldepth_b200.models_meta import ModelParameters
+    rs = np.random.RandomState(0)
+    B, H, W, K, R = 2, 32, 32, 5, 100
+    gt = rs.rand(B, H, W).astype(np.float32)
+    mask = (rs.rand(B, H, W) > 0.2).astype(np.float32)
+    gt_d, mask_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(mask).to(cuda_device)
+    for cls in (sampling.MaskedRandomSamplingStrategy, sampling.ThresholdedMaskedRandomSamplingStrategy,
+                sampling.InformationScoreBasedSampling):
+        a = cls(ModelParameters(ranking_size=K), rng="philox", seed=9)
+        b = cls(ModelParameters(ranking_size=K), rng="philox", seed=9)
+        fast = a.sample_batch(gt_d, mask_d, R)
+        n = int(R * b._default_factor)
+        cand = b.draw_candidates(gt_d, mask_d, n)
+        staged, _ = ops.select_top(b.score_candidates(cand, gt_d), cand, R)
+        assert torch.equal(fast, staged)

@@ -19,9 +19,8 @@ struct ListParams {
   float* rank_out;             // [B, n, K, 2] nullable
   uint64_t* score_keys;        // [B, n] ordered scores (score mode of the small kernel)
   ScoreCfg score_cfg;
-  // optional indirection: list l of image b redraws candidate list_map[b*map_stride + map_len[b]-1-l]
+  // optional indirection: list l of image b redraws candidate list_map[b*map_stride + l]
   const uint32_t* list_map;
-  const int* map_len;
   size_t map_stride;
   int32_t* sel_out;            // [B, n, K] nullable
   float* per_list;             // [B*n] nullable

@@ -63,14 +63,10 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
   }
 
   // Philox list id of the l-th list of this image: l itself, or the l-th best candidate of a
-  // previous scoring pass (list_map holds candidates in ascending score order; read backwards)
+  // previous scoring pass
   const uint32_t* __restrict__ lmap = nullptr;
-  int lmap_last = 0;
-  if (SRC == SRC_PHILOX_TAB && P.list_map != nullptr) {
-    lmap = P.list_map + (size_t)b * P.map_stride;
-    lmap_last = P.map_len[b] - 1;
-  }
-  auto philox_list = [&](int l) -> int { return lmap ? (int)__ldg(lmap + (lmap_last - l)) : l; };
+  if (SRC == SRC_PHILOX_TAB && P.list_map != nullptr) lmap = P.list_map + (size_t)b * P.map_stride;
+  auto philox_list = [&](int l) -> int { return lmap ? (int)__ldg(lmap + l) : l; };
 
   // software pipeline of the table path: the draws and table gathers of the NEXT list are issued
   // before the current list is ordered / scored, so their latency hides behind that work

@@ -17,83 +17,104 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // elements per CTA
 constexpr int RS_BINS = 256;
 
 struct SegInfo {
-  const int* len_dev;  // per-image live length (nullable)
-  int len_fixed;       // used when len_dev == nullptr
-  size_t stride;       // elements between consecutive images
+  const int* len_dev;                 // per-image live length (nullable)
+  int len_fixed;                      // used when len_dev == nullptr
+  size_t stride;                      // elements between consecutive images
+  const unsigned long long* varying;  // per-image mask of key bits that differ between live keys (nullable)
   __device__ __forceinline__ int len(int b) const { return len_dev ? len_dev[b] : len_fixed; }
+  // a pass over a byte in which all live keys agree cannot reorder anything: it is skipped, and the
+  // ping-pong parity of an image is the number of passes it really executed
+  __device__ __forceinline__ bool skip(int b, int pass) const {
+    return varying != nullptr && ((varying[b] >> (8 * pass)) & 0xFFull) == 0ull;
+  }
+  __device__ __forceinline__ int parity(int b, int pass) const {  // executed passes before `pass`
+    if (varying == nullptr) return pass & 1;
+    const unsigned long long v = varying[b];
+    int c = 0;
+    for (int p = 0; p < pass; ++p) c += ((v >> (8 * p)) & 0xFFull) ? 1 : 0;
+    return c & 1;
+  }
 };
 
-// per (image, tile) digit histogram -> hist[(b * RS_BINS + digit) * nblk + tile]
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, SegInfo seg, int shift,
+// per (image, tile) digit histogram -> hist[(b * nblk + tile) * RS_BINS + digit]
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys_a,
+                                                             const uint64_t* __restrict__ keys_b, SegInfo seg, int pass,
                                                              int nblk, int* __restrict__ hist) {
   __shared__ int s_h[RS_BINS];
   const int b = blockIdx.y, tile = blockIdx.x;
+  if (seg.skip(b, pass)) return;
   const int n = seg.len(b);
+  const int base = tile * RS_TILE;
+  if (base >= n) return;
   s_h[threadIdx.x] = 0;
   __syncthreads();
-  const int base = tile * RS_TILE;
-  if (base < n) {
-    const uint64_t* k = keys + (size_t)b * seg.stride;
+  const uint64_t* k = (seg.parity(b, pass) ? keys_b : keys_a) + (size_t)b * seg.stride;
+  const int shift = pass * 8;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-      const int idx = base + i * RS_THREADS + threadIdx.x;
-      if (idx < n) atomicAdd(&s_h[(int)((k[idx] >> shift) & 0xFF)], 1);
-    }
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int idx = base + i * RS_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&s_h[(int)((k[idx] >> shift) & 0xFF)], 1);
   }
   __syncthreads();
-  hist[((size_t)b * RS_BINS + threadIdx.x) * nblk + tile] = s_h[threadIdx.x];
+  hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x] = s_h[threadIdx.x];
 }
 
-// one CTA per image: exclusive scan of its RS_BINS * nblk counts in (digit, tile) order
-__global__ void __launch_bounds__(1024) rs_scan_kernel(int* __restrict__ hist, int nblk) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  int* h = hist + (size_t)blockIdx.x * RS_BINS * nblk;
-  const int total = RS_BINS * nblk;
-  if (threadIdx.x == 0) s_carry = 0;
+// one CTA per image, thread d owns digit d: running prefix over the live tiles (coalesced across
+// digits), then an exclusive scan of the 256 digit totals -> dig_off[b][d]
+__global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist, int* __restrict__ dig_off, SegInfo seg,
+                                                          int pass, int nblk) {
+  __shared__ int s_tot[RS_BINS];
+  const int b = blockIdx.x;
+  if (seg.skip(b, pass)) return;
+  const int n = seg.len(b);
+  const int live = (n + RS_TILE - 1) / RS_TILE;
+  int* h = hist + (size_t)b * nblk * RS_BINS + threadIdx.x;
+  int run = 0;
+#pragma unroll 4
+  for (int t = 0; t < live; ++t) {
+    const int c = h[(size_t)t * RS_BINS];
+    h[(size_t)t * RS_BINS] = run;
+    run += c;
+  }
+  s_tot[threadIdx.x] = run;
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < total; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int c = (i < total) ? h[i] : 0;
-    int inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
+  // exclusive scan of 256 totals (Hillis-Steele in shared memory)
+  for (int o = 1; o < RS_BINS; o <<= 1) {
+    const int v = (threadIdx.x >= o) ? s_tot[threadIdx.x - o] : 0;
     __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < wid; ++w) woff += s_warp[w];
-    const int carry = s_carry;
-    if (i < total) h[i] = carry + woff + inc - c;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + woff + inc;
+    s_tot[threadIdx.x] += v;
     __syncthreads();
   }
+  dig_off[b * RS_BINS + threadIdx.x] = s_tot[threadIdx.x] - run;
 }
 
 // stable scatter: elements of a tile are ranked round by round (256 consecutive elements per round);
 // inside a round __match_any_sync gives the rank among equal digits of a warp, per-warp digit counts
 // give the rank across warps, running counters carry over rounds.
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in,
-                                                                uint64_t* __restrict__ keys_out,
-                                                                uint32_t* __restrict__ vals_out, SegInfo seg, int shift,
-                                                                int nblk, const int* __restrict__ hist) {
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
+                                                                uint64_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
+                                                                SegInfo seg, int pass, int nblk,
+                                                                const int* __restrict__ hist,
+                                                                const int* __restrict__ dig_off) {
   __shared__ int s_base[RS_BINS];              // global offset of (digit, this tile) + elements already placed
   __shared__ int s_wcnt[RS_THREADS / 32][RS_BINS];
   const int b = blockIdx.y, tile = blockIdx.x;
+  if (seg.skip(b, pass)) return;
   const int n = seg.len(b);
   const int base = tile * RS_TILE;
   if (base >= n) return;
+  const bool flip = seg.parity(b, pass) != 0;
+  const size_t off = (size_t)b * seg.stride;
+  const uint64_t* keys_in = (flip ? keys_b : keys_a) + off;
+  const uint32_t* vals_in = (flip ? vals_b : vals_a) + off;
+  uint64_t* keys_out = (flip ? keys_a : keys_b) + off;
+  uint32_t* vals_out = (flip ? vals_a : vals_b) + off;
+  const int shift = pass * 8;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  s_base[threadIdx.x] = hist[((size_t)b * RS_BINS + threadIdx.x) * nblk + tile];
+  s_base[threadIdx.x] = dig_off[b * RS_BINS + threadIdx.x] + hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x];
 #pragma unroll
   for (int w = 0; w < RS_THREADS / 32; ++w) s_wcnt[w][threadIdx.x] = 0;
   __syncthreads();
-  const size_t off = (size_t)b * seg.stride;
   for (int r = 0; r < RS_ITEMS; ++r) {
     const int idx = base + r * RS_THREADS + threadIdx.x;
     const bool on = idx < n;
@@ -101,8 +122,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
     uint32_t v = 0;
     int d = 0;
     if (on) {
-      k = keys_in[off + idx];
-      v = vals_in[off + idx];
+      k = keys_in[idx];
+      v = vals_in[idx];
       d = (int)((k >> shift) & 0xFF);
     }
     // lanes past the end use digit 256 + lane so that they match nobody
@@ -114,8 +135,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
       int pre = 0;
       for (int w = 0; w < wid; ++w) pre += s_wcnt[w][d];
       const int pos = s_base[d] + pre + rank_w;
-      keys_out[off + pos] = k;
-      vals_out[off + pos] = v;
+      keys_out[pos] = k;
+      vals_out[pos] = v;
     }
     __syncthreads();
     {
@@ -131,33 +152,33 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
   }
 }
 
-// Sorts (keys, vals) ascending, stable, per image.  Eight 8-bit passes ping-pong between the two
-// buffer pairs; the result ends in (keys, vals).  hist: int[B * 256 * nblk] scratch.
+// Sorts (keys, vals) ascending, stable, per image, with eight 8-bit passes that ping-pong between the
+// (a) and (b) buffer pairs.  Without `varying` the result ends in (a).  With `varying` (per-image mask of
+// non-constant key bits) passes over constant bytes are skipped per image and the result of image b sits in
+// (a) if it executed an even number of passes, else in (b): see seg_sorted_in_b().
+// hist: int[B * nblk * 256 + B * 256] scratch.
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                   const int* len_dev, int len_max, size_t stride, int B, int* hist, cudaStream_t st) {
+                   const int* len_dev, int len_max, size_t stride, int B, int* hist,
+                   const unsigned long long* varying, cudaStream_t st) {
   if (len_max <= 0) return PLD_OK;
   const int nblk = (len_max + RS_TILE - 1) / RS_TILE;
-  SegInfo seg{len_dev, len_max, stride};
+  SegInfo seg{len_dev, len_max, stride, varying};
+  int* dig_off = hist + (size_t)B * nblk * RS_BINS;
   dim3 grid((unsigned)nblk, (unsigned)B);
-  uint64_t *ki = keys, *ko = keys_tmp;
-  uint32_t *vi = vals, *vo = vals_tmp;
   for (int pass = 0; pass < 8; ++pass) {
-    const int shift = pass * 8;
-    rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(ki, seg, shift, nblk, hist);
+    rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(keys, keys_tmp, seg, pass, nblk, hist);
     PLD_CHECK_LAUNCH();
-    rs_scan_kernel<<<B, 1024, 0, st>>>(hist, nblk);
+    rs_scan_kernel<<<B, RS_BINS, 0, st>>>(hist, dig_off, seg, pass, nblk);
     PLD_CHECK_LAUNCH();
-    rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(ki, vi, ko, vo, seg, shift, nblk, hist);
+    rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(keys, vals, keys_tmp, vals_tmp, seg, pass, nblk, hist, dig_off);
     PLD_CHECK_LAUNCH();
-    uint64_t* tk = ki; ki = ko; ko = tk;
-    uint32_t* tv = vi; vi = vo; vo = tv;
   }
   return PLD_OK;
 }
 
 size_t seg_radix_sort_hist_bytes(int len_max, int B) {
   const int nblk = (len_max + RS_TILE - 1) / RS_TILE;
-  return sizeof(int) * (size_t)B * RS_BINS * (size_t)(nblk > 0 ? nblk : 1);
+  return sizeof(int) * (size_t)B * RS_BINS * ((size_t)(nblk > 0 ? nblk : 1) + 1);
 }
 
 }  // namespace pld

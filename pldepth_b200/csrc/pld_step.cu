@@ -18,7 +18,8 @@ int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cud
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                   const int* len_dev, int len_max, size_t stride, int B, int* hist, cudaStream_t st);
+                   const int* len_dev, int len_max, size_t stride, int B, int* hist,
+                   const unsigned long long* varying, cudaStream_t st);
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
 
 constexpr int PC_THREADS = 256;
@@ -174,11 +175,13 @@ __global__ void __launch_bounds__(256) gt_minmax_step_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B) {
+__global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B,
+                                                       unsigned long long* bits_or, unsigned long long* bits_and) {
   for (int i = blockIdx.x * 256 + threadIdx.x; i < B * SEL_BINS; i += gridDim.x * 256) hist[i] = 0u;
-  if (blockIdx.x == 0 && (int)threadIdx.x < B) { prefix[threadIdx.x] = 0ull; remaining[threadIdx.x] = R; }
   if (blockIdx.x == 0)
-    for (int i = 256 + threadIdx.x; i < B; i += 256) { prefix[i] = 0ull; remaining[i] = R; }
+    for (int i = threadIdx.x; i < B; i += 256) {
+      prefix[i] = 0ull; remaining[i] = R; bits_or[i] = 0ull; bits_and[i] = ~0ull;
+    }
 }
 
 __global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restrict__ keys, int n, int pass,
@@ -263,7 +266,9 @@ __global__ void __launch_bounds__(SC_THREADS) sel_count_kernel(const uint64_t* _
 __global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t* __restrict__ keys, int n, int ntiles,
                                                                 const uint64_t* __restrict__ prefix,
                                                                 const int* __restrict__ counts, uint64_t* __restrict__ keys_s,
-                                                                uint32_t* __restrict__ vals_s, int* __restrict__ n_surv) {
+                                                                uint32_t* __restrict__ vals_s, int* __restrict__ n_surv,
+                                                                unsigned long long* __restrict__ bits_or,
+                                                                unsigned long long* __restrict__ bits_and) {
   __shared__ int s_warp[SC_THREADS / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   int pre = 0, all = 0;
@@ -296,23 +301,53 @@ __global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t*
   for (int i = 0; i < wid; ++i) rank += s_warp[i];
   const uint32_t lt = (1u << lane) - 1u;
   const size_t off = (size_t)b * n;
+  unsigned long long vor = 0ull, vand = ~0ull;
 #pragma unroll
   for (int i = 0; i < SC_ITEMS; ++i) {
     if ((bal[i] >> lane) & 1u) {
       const int pos = rank + __popc(bal[i] & lt);
       keys_s[off + pos] = kv[i];
       vals_s[off + pos] = (uint32_t)(wbase + i * 32 + lane);
+      vor |= kv[i];
+      vand &= kv[i];
     }
     rank += __popc(bal[i]);
   }
+  // which key bits differ between survivors: OR / AND over all of them (one atomic pair per warp)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+  }
+  if (lane == 0 && wcount > 0) {
+    atomicOr(bits_or + b, vor);
+    atomicAnd(bits_and + b, vand);
+  }
 }
 
-__global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restrict__ vals_s, const int* __restrict__ n_surv,
-                                                        int n, int R, int32_t* __restrict__ order_out) {
+__global__ void sel_varying_kernel(const unsigned long long* bits_or, const unsigned long long* bits_and,
+                                   unsigned long long* varying, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) varying[b] = bits_or[b] ^ bits_and[b];
+}
+
+// kept candidates in final order (score descending): tail of the sorted survivors read backwards, taken from
+// whichever ping-pong buffer the image's last executed pass wrote
+__global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
+                                                        const unsigned long long* __restrict__ varying,
+                                                        const int* __restrict__ n_surv, int n, int R,
+                                                        uint32_t* __restrict__ order, int32_t* __restrict__ order_out) {
   const int b = blockIdx.y;
   const int last = n_surv[b] - 1;
-  for (int j = blockIdx.x * 256 + threadIdx.x; j < R; j += gridDim.x * 256)
-    order_out[(size_t)b * R + j] = (int32_t)vals_s[(size_t)b * n + (last - j)];
+  const unsigned long long v = varying[b];
+  int passes = 0;
+  for (int p = 0; p < 8; ++p) passes += ((v >> (8 * p)) & 0xFFull) ? 1 : 0;
+  const uint32_t* src = ((passes & 1) ? vals_b : vals_a) + (size_t)b * n;
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < R; j += gridDim.x * 256) {
+    const uint32_t c = src[last - j];
+    order[(size_t)b * R + j] = c;
+    if (order_out != nullptr) order_out[(size_t)b * R + j] = (int32_t)c;
+  }
 }
 
 }  // namespace pld
@@ -427,6 +462,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const size_t o_v0 = take(sizeof(uint32_t) * total);
   const size_t o_v1 = take(sizeof(uint32_t) * total);
   const size_t o_rhist = take(seg_radix_sort_hist_bytes(n, B));
+  const size_t o_bits = take(sizeof(unsigned long long) * 3 * (size_t)B);
+  const size_t o_order = take(sizeof(uint32_t) * (size_t)B * R);
   const size_t o_tab = take(sizeof(float2) * (size_t)B * tstride);
   int rc = ctx->ensure_scratch(off);
   if (rc) return rc;
@@ -445,6 +482,10 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   uint32_t* v0 = (uint32_t*)(sb + o_v0);
   uint32_t* v1 = (uint32_t*)(sb + o_v1);
   int* rhist = (int*)(sb + o_rhist);
+  unsigned long long* bits_or = (unsigned long long*)(sb + o_bits);
+  unsigned long long* bits_and = bits_or + B;
+  unsigned long long* varying = bits_or + 2 * B;
+  uint32_t* order = (uint32_t*)(sb + o_order);
   float2* table = (float2*)(sb + o_tab);
   const int per_image_cap = (ctx->num_sms * 8 + B - 1) / B;
   rc = ctx->ensure_partials(per_image_cap * B + B);
@@ -490,7 +531,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   // 3. radix top-R selection -> survivors in candidate order
   int gsel = (n + 255) / 256;
   if (gsel > per_image_cap) gsel = per_image_cap;
-  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B);
+  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and);
   PLD_CHECK_LAUNCH();
   for (int pass = 0; pass < 3; ++pass) {
     sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
@@ -501,23 +542,25 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   dim3 tgrid((unsigned)ntiles, (unsigned)B);
   sel_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt);
   PLD_CHECK_LAUNCH();
-  sel_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt, k0, v0, n_surv);
+  sel_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt, k0, v0, n_surv, bits_or, bits_and);
+  PLD_CHECK_LAUNCH();
+  sel_varying_kernel<<<(B + 255) / 256, 256, 0, st>>>(bits_or, bits_and, varying, B);
   PLD_CHECK_LAUNCH();
 
   // 4. full order of the survivors (ascending, stable); the best R are the tail read backwards
-  rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, st);
+  rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, varying, st);
   if (rc) return rc;
-  if (order_out != nullptr) {
+  {
     int go = (R + 255) / 256;
     if (go > per_image_cap) go = per_image_cap;
-    sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, n_surv, n, R, order_out);
+    sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, v1, varying, n_surv, n, R, order, order_out);
     PLD_CHECK_LAUNCH();
   }
 
   // 5. redraw the kept lists from their Philox ids: emit rankings, loss and gradient
   P.score_keys = nullptr;
   P.n = R;
-  P.list_map = v0; P.map_len = n_surv; P.map_stride = (size_t)n;
+  P.list_map = order; P.map_stride = (size_t)R;
   P.rank_out = rankings; P.per_list = per_list; P.grad = grad; P.loss = loss; P.loss_sum = loss_sum;
   const bool do_loss = loss != nullptr;
   if (do_loss && grad != nullptr && ctx->deterministic) {

@@ -17,7 +17,11 @@ from ._lib import Context, check, c_void_p
 
 class FusedPLStep(object):
     def __init__(self, ranking_size, rankings_per_image, seed=0, emit_rankings=True, global_batch=None,
-                 image_base=0):
+                 image_base=0, strategy="purely", candidate_factor=None, threshold=0.03, equality_penalty=-1000,
+                 promotion="nep50"):
+        """``strategy``: 'purely' (core sampler, exactly R lists/image -- the headline path) or one of
+        'masked' / 'thresholded' / 'information' (R best of int(R * candidate_factor) candidates, default
+        factors 1.5 / 1.5 / 5 as in sampling.py:157,190,218)."""
         self.K = int(ranking_size)
         self.R = int(rankings_per_image)
         self.seed = int(seed)
@@ -26,6 +30,14 @@ class FusedPLStep(object):
         self.image_base = int(image_base)
         self.step_index = 0
         self._buf = None
+        if strategy not in ("purely", "masked", "thresholded", "information"):
+            raise ValueError("unknown strategy %r" % (strategy,))
+        self.strategy = strategy
+        default_f = {"purely": 1.0, "masked": 1.5, "thresholded": 1.5, "information": 5}[strategy]
+        self.n_candidates = int(self.R * (default_f if candidate_factor is None else candidate_factor))
+        self.threshold, self.equality_penalty, self.promotion = threshold, equality_penalty, promotion
+        if strategy != "purely" and (self.K > 16 or self.n_candidates < self.R):
+            raise ValueError("scored strategies need ranking_size <= 16 and candidate_factor >= 1 on the fused path")
 
     def _buffers(self, B, H, W, Hm, Wm, dev):
         key = (B, H, W, Hm, Wm, dev)
@@ -56,6 +68,16 @@ class FusedPLStep(object):
         gb = self.global_batch if self.global_batch else B
         scale = 1.0 / (float(gb) * float(self.R))
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+        if self.strategy != "purely":
+            from ._lib import STRATEGY, PROMOTION
+            check(lib.pld_fused_step_scored(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K,
+                                            self.n_candidates, self.R, STRATEGY[self.strategy], float(self.threshold),
+                                            float(self.equality_penalty), PROMOTION[self.promotion], self.seed,
+                                            self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
+                                            c_void_p(None), p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]),
+                                            c_void_p(None), p(buf["grad"]), stream))
+            self.step_index += 1
+            return buf
         if self.K <= 16:
             # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
             check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,

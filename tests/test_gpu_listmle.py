@@ -274,3 +274,19 @@ def test_deterministic_mode_is_bit_reproducible(cuda_device):
         assert_close(grads[0].cpu().numpy(), want_grad, "deterministic gradient")
     finally:
         ctx.set_deterministic(False)
+
+
+def test_fused_step_object_with_strategy(cuda_device):
+    from pldepth_b200 import ops
+    from pldepth_b200.step import FusedPLStep
+    from tests.test_gpu_sampler import make_maps
+    B, H, W, K, R = 2, 32, 32, 5, 200
+    gt, mask = make_maps(H, W, H, W, 2, B)
+    pred = np.random.RandomState(0).randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    st = FusedPLStep(K, R, seed=3, strategy="thresholded")
+    out = st.run(gt_d, mask_d, pred_d)
+    ref = ops.fused_step_scored(mask_d, gt_d, pred_d, K, int(R * 1.5), R, "thresholded", seed=3, offset=0)
+    assert torch.equal(out["rankings"], ref["rankings"]) and out["loss"].item() == ref["loss"].item()
+    with pytest.raises(ValueError):
+        FusedPLStep(20, R, strategy="masked")

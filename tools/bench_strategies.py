@@ -38,9 +38,14 @@ def main():
         s = cls(mp, rng="philox", seed=1)
         f = 1.0 if name.startswith("purely") else None
 
-        def step():
-            y = s.sample_batch(gt, mask, R, f)
-            return ops.listmle_fwd_bwd(y, pred, B, K, 1.0 / (B * y.shape[1]))
+        def step(s=s, f=f, name=name):
+            if name.startswith("purely"):
+                y = s.sample_batch(gt, mask, R, f)
+                return ops.listmle_fwd_bwd(y, pred, B, K, 1.0 / (B * y.shape[1]))
+            n = int(R * s._default_factor)          # one call: score pass, top-R, redraw + loss + gradient
+            return ops.fused_step_scored(mask, gt, pred, K, n, R, s._strategy, 0.03, -1000, "nep50", seed=1,
+                                         offset=step.i)
+        step.i = 0
         for _ in range(3):
             step()
         torch.cuda.synchronize()

@@ -225,15 +225,27 @@ def run_b200(args):
     step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B)
     loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    pending = []
+
     def one_step(i):
         s = sets[i % n_sets]
         out = step.run(s["gt"], s["mask"], s["pred"], out=s["out"])
         if world > 1:
-            dist.all_reduce(out["loss_sum"])          # the path's only exchange: one f64
+            # the path's only exchange: one f64 per step.  Nothing downstream of the step depends on it
+            # (the gradient already carries the global 1/L), so it is issued asynchronously and overlaps
+            # the next step; every reduction is waited for before the timed region closes.
+            pending.append(dist.all_reduce(out["loss_sum"], async_op=True))
+            if len(pending) > n_sets - 1:
+                pending.pop(0).wait()
         return out
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     for i in range(max(3, args.warmup)):
         one_step(i)
+    drain()
     torch.cuda.synchronize()
     step.check(dev)
 
@@ -250,6 +262,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -259,31 +272,37 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.rows.clear()
     e0.record()
     for i in range(args.steps):
         if graphs is not None:
             graphs[i % n_sets].replay()
         else:
             one_step(i)
+    drain()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     if graphs is not None:
         launches = args.steps * 3
-    # keep the clock sampler running over a second identical timed burst if the first was too
-    # short to catch a sample (nvidia-smi takes ~50 ms per query)
-    t_end = time.time() + 0.7
-    while time.time() < t_end and len(sampler.rows) < 2:
-        for i in range(args.steps):
-            one_step(i)
-        torch.cuda.synchronize()
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+    # clocks under load: nvidia-smi needs ~50-100 ms per query and the timed region lasts only a few ms, so the
+    # SAME steps keep running for ~0.7 s right after it while the sampler polls.  The burst length is derived
+    # from the max-reduced time, hence identical on every rank (each step carries a collective).
+    n_burst = max(args.steps, min(20000, int(700.0 / max(ms_total / args.steps, 1e-3))))
+    for i in range(n_burst):
+        if graphs is not None:
+            graphs[i % n_sets].replay()
+        else:
+            one_step(i)
+    drain()
+    torch.cuda.synchronize()
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
     step.check(dev)
 
     # ---- dominant kernel alone: the library records CUDA events around the list kernel of every
@@ -294,6 +313,7 @@ def run_b200(args):
     ctx.kernel_timing(n_k)
     for i in range(n_k):
         one_step(i)
+    drain()
     torch.cuda.synchronize()
     kms = ctx.kernel_times(n_k)
     ctx.kernel_timing(0)

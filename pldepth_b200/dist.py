@@ -34,7 +34,7 @@ class ShardedPLStep(object):
     """
 
     def __init__(self, ranking_size, rankings_per_image, global_batch, seed=0, group=None, local_step=None,
-                 emit_rankings=True):
+                 emit_rankings=True, async_loss=False):
         self.K = int(ranking_size)
         self.R = int(rankings_per_image)
         self.global_batch = int(global_batch)
@@ -46,6 +46,7 @@ class ShardedPLStep(object):
         self._fused = None
         self.seed = int(seed)
         self.emit_rankings = emit_rankings
+        self.async_loss = bool(async_loss)
 
     def _default_step(self, gt, mask, pred, image_base, global_batch):
         from .step import FusedPLStep
@@ -63,10 +64,21 @@ class ShardedPLStep(object):
         step = self._local_step or self._default_step
         out = step(gt_local, mask_local, pred_local, self.lo, self.global_batch)
         total = out["loss_sum"].clone()
+        work = None
         if self.world > 1:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+            # nothing downstream of the step depends on the reduced loss (the local gradient already carries
+            # the global 1/L), so with async_loss the reduction overlaps whatever the caller enqueues next
+            work = dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_loss)
+        if work is not None and self.async_loss:
+            return dict(loss=None, loss_sum=total, loss_work=work, grad=out["grad"], rankings=out.get("rankings"))
         loss = (total / float(self.global_batch * self.R)).to(torch.float32)
         return dict(loss=loss, loss_sum=total, grad=out["grad"], rankings=out.get("rankings"))
+
+    def finish_loss(self, result):
+        """Wait for an asynchronous loss reduction and return the global mean loss."""
+        if result.get("loss_work") is not None:
+            result["loss_work"].wait()
+        return (result["loss_sum"] / float(self.global_batch * self.R)).to(torch.float32)
 
     def gather_grad(self, grad_local):
         """Replicated dense gradient [B_global, ...] from the disjoint slices (all-gather)."""

@@ -95,11 +95,29 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   const float* g = gt + (size_t)b * HW;
   if (identity_scale && total == Nm) {
     const float* s = pred + (size_t)b * HW;
-    // coalesced: thread t handles elements chunk*CHUNK + i*THREADS + t
+    const bool vec = ((Nm & 3) == 0) && ((table_stride & 1) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(table) & 15) == 0;
+    if (vec) {
+      // 4 pixels per thread and iteration: two 16-byte loads, two 16-byte stores, all coalesced
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* t4 = reinterpret_cast<float4*>(tab);
+#pragma unroll
+      for (int i = 0; i < PC_ITEMS / 4; ++i) {
+        const int q = chunk * (PC_CHUNK / 4) + i * PC_THREADS + threadIdx.x;   // index of a 4-pixel group
+        if (q * 4 < Nm) {
+          const float4 a = __ldg(g4 + q), c = __ldg(s4 + q);
+          t4[2 * q] = make_float4(a.x, c.x, a.y, c.y);
+          t4[2 * q + 1] = make_float4(a.z, c.z, a.w, c.w);
+        }
+      }
+    } else {
 #pragma unroll 4
-    for (int i = 0; i < PC_ITEMS; ++i) {
-      const int j = chunk * PC_CHUNK + i * PC_THREADS + threadIdx.x;
-      if (j < Nm) tab[j] = make_float2(__ldg(g + j), __ldg(s + j));
+      for (int i = 0; i < PC_ITEMS; ++i) {
+        const int j = chunk * PC_CHUNK + i * PC_THREADS + threadIdx.x;
+        if (j < Nm) tab[j] = make_float2(__ldg(g + j), __ldg(s + j));
+      }
     }
     if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
     return;

@@ -290,3 +290,64 @@ def test_fused_step_object_with_strategy(cuda_device):
     assert torch.equal(out["rankings"], ref["rankings"]) and out["loss"].item() == ref["loss"].item()
     with pytest.raises(ValueError):
         FusedPLStep(20, R, strategy="masked")
+
+
+@pytest.mark.parametrize("B,H,W,K,n", [(1, 7, 9, 3, 1), (2, 5, 5, 1, 40), (1, 31, 33, 5, 255), (3, 17, 19, 16, 257),
+                                       (2, 64, 64, 5, 0)])
+def test_edge_shapes_one_call_step(cuda_device, B, H, W, K, n):
+    """Ragged / tiny / empty shapes: odd pixel counts (scalar table path), one list, K = 1, n = 0."""
+    from pldepth_b200 import ops
+    from tests.test_gpu_sampler import make_maps
+    gt, mask = make_maps(H, W, H, W, H + W, B, hole=False)
+    pred = np.random.RandomState(0).randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    loss, loss_sum, grad, rank, pl, nv = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=1, scale=1.0 / max(1, B * n),
+                                                        want_per_list=True)
+    ops.check_status(cuda_device)
+    assert (nv < 0).all()
+    if n == 0:
+        assert loss.item() == 0 and rank.numel() == 0 and float(grad.abs().sum()) == 0
+        return
+    want_loss, want_grad, want_pl = lo.hourglass_nll(rank.cpu().numpy(), pred, B, K)
+    assert_close(pl.cpu().numpy(), want_pl, "per-list") if K > 1 else None
+    assert abs(loss.item() - want_loss) <= 1e-5 * max(abs(want_loss), 1e-30)
+    if K > 1:
+        assert_close(grad.cpu().numpy(), want_grad, "gradient")
+    else:
+        assert float(grad.abs().max()) == 0 and loss.item() == 0     # K = 1: NLL and gradient are exactly 0
+
+
+def test_scored_step_edges(cuda_device):
+    """R == n (keep everything, pure ordering), R == 1, K == 1 (all scores equal: order = index descending)."""
+    from pldepth_b200 import ops
+    from tests.test_gpu_sampler import make_maps
+    B, H, W = 2, 20, 20
+    gt, mask = make_maps(H, W, H, W, 3, B)
+    gt_d, mask_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(mask).to(cuda_device)
+    for K, n, R in ((5, 64, 64), (5, 300, 1), (1, 50, 20)):
+        out = ops.fused_step_scored(mask_d, gt_d, None, K, n, R, "thresholded", seed=2, want_order=True)
+        vf, nv = ops.mask_compact(mask_d, H, W)
+        cand, _ = ops.sample_lists_philox(gt_d, vf, nv, K, n, 2, 0, 0)
+        top, order = ops.select_top(ops.score_lists(cand, "thresholded"), cand, R, want_order=True)
+        assert torch.equal(out["order"], order) and torch.equal(out["rankings"], top)
+        if K == 1:
+            assert order[0].tolist() == list(range(n - 1, n - 1 - R, -1))
+
+
+def test_maximum_map_size(cuda_device):
+    """PLD_MAX_PIXELS = 2^23 pixels (flat indices are packed into 23 bits of the sort key): 4096 x 2048."""
+    from pldepth_b200 import ops
+    H, W, K, n = 4096, 2048, 5, 2000
+    g = torch.rand((1, H, W), device=cuda_device)
+    g[0, -1, -1] = 2.0                                   # the last pixel is the deepest
+    mask = torch.ones((1, H, W), device=cuda_device)
+    pred = torch.randn((1, H, W, 1), device=cuda_device)
+    loss, _, grad, rank, _, nv = ops.fused_step(mask, g, pred, K, n, seed=5)
+    ops.check_status(cuda_device)
+    assert int(nv[0]) == -(H * W)
+    idx = rank[0, :, :, 0].long()
+    assert int(idx.max()) < H * W and int(idx.max()) > (H * W) * 0.99        # draws reach the top of the range
+    assert bool((torch.gather(g.reshape(-1), 0, idx.reshape(-1)).reshape(n, K) == rank[0, :, :, 1]).all())
+    with pytest.raises(Exception):
+        ops.fused_step(torch.ones((1, 4097, 2048), device=cuda_device), torch.rand((1, 4097, 2048), device=cuda_device),
+                       torch.randn((1, 4097, 2048, 1), device=cuda_device), K, 10, seed=1)

@@ -185,7 +185,6 @@ int pld_fused_sample_loss_bwd(pld_ctx* ctx, const float* gt, const int32_t* vali
  * its gradient (nll_loss.py:32-62).  Three launches: mask analysis (+ zeroing of grad), per-image
  * 8-byte lookup tables in context scratch, fused list kernel.  Outputs are identical to
  * pld_mask_compact + pld_fused_sample_loss_bwd with the same (seed, offset, image_base).
- * ranking_size 1..16 only (larger K: use the staged calls).
  *   mask f32[B,Hm,Wm], gt f32[B,H*W], pred f32[B,H*W]
  *   -> n_valid i32[B] (nullable; negative = identity table, see pld_mask_compact),
  *      rankings f32[B,n,K,2] (nullable), loss f32[1], loss_sum f64[1] (nullable),

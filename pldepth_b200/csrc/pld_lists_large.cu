@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
       int p[IPL];
       float lab[IPL];
       uint32_t inval = 0;
+      uint32_t s_tab[IPL];   // predictions delivered by the (gt, pred) table (bits), sorted order
+      bool have_s = false;
 
       if (SRC == SRC_FED_RANK) {
         const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) + list_id * K;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
         int sel[IPL];
 #pragma unroll
         for (int i = 0; i < IPL; ++i) sel[i] = 0;
-        if (SRC == SRC_PHILOX) {
+        if (SRC == SRC_PHILOX || SRC == SRC_PHILOX_TAB) {
           bool rej = false;
 #pragma unroll
           for (int q = 0; q < IPL / 4; ++q) {
@@ -245,17 +247,44 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
           }
         }
         // pad slots read entry 0 (always valid) and get the smallest key, so they sort last
-        int qv[IPL];
+        if (SRC == SRC_PHILOX_TAB) {
+          // per-image 8-byte lookup table (pld_step.cu): one gather per draw
+          const float2* __restrict__ tab = P.table + (size_t)b * P.table_stride;
+          float2 t[IPL];
 #pragma unroll
-        for (int i = 0; i < IPL; ++i) qv[i] = identity ? sel[i] : __ldg(vflat + sel[i]);
+          for (int i = 0; i < IPL; ++i) t[i] = __ldg(tab + sel[i]);
+          if (identity) {  // entry j = (gt[j], pred[j]); the prediction rides through the sort as payload
 #pragma unroll
-        for (int i = 0; i < IPL; ++i) {
-          const float g = __ldg(gt + qv[i]);
-          const bool on = (emask >> i) & 1u;
-          khi[i] = on ? float_to_ordered(g) : 0u;
-          klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)qv[i]) : 0u;
+            for (int i = 0; i < IPL; ++i) {
+              const bool on = (emask >> i) & 1u;
+              khi[i] = on ? float_to_ordered(t[i].x) : 0u;
+              klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)sel[i]) : 0u;
+              s_tab[i] = __float_as_uint(t[i].y);
+            }
+            bitonic_desc<LPL, IPL, true>(khi, klo, s_tab, gl);
+            have_s = true;
+          } else {         // entry j = (bits of flat index p_j, gt[p_j])
+#pragma unroll
+            for (int i = 0; i < IPL; ++i) {
+              const bool on = (emask >> i) & 1u;
+              khi[i] = on ? float_to_ordered(t[i].y) : 0u;
+              klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)__float_as_int(t[i].x)) : 0u;
+            }
+            bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
+          }
+        } else {
+          int qv[IPL];
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) qv[i] = identity ? sel[i] : __ldg(vflat + sel[i]);
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) {
+            const float g = __ldg(gt + qv[i]);
+            const bool on = (emask >> i) & 1u;
+            khi[i] = on ? float_to_ordered(g) : 0u;
+            klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)qv[i]) : 0u;
+          }
+          bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
         }
-        bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
           p[i] = (int)(klo[i] & 0x7FFFFFu);
@@ -281,7 +310,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
         float m = -3.402823466e38f;
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
-          const float sv = __ldg(pred + p[i]);  // pad slots hold p == 0: a valid address
+          const float sv = have_s ? __uint_as_float(s_tab[i]) : __ldg(pred + p[i]);  // pads: p == 0 is valid
           s[i] = ((emask >> i) & 1u) ? (((inval >> i) & 1u) ? PLD_LOG_EPS : sv) : -3.402823466e38f;
           m = fmaxf(m, s[i]);
         }
@@ -333,6 +362,8 @@ static int launch_large_cfg(const ListParams& P, int src, bool loss, dim3 grid, 
   } else if (src == SRC_FED_SEL) {
     if (loss) lists_large_kernel<LPL, IPL, SRC_FED_SEL, true><<<grid, 256, 0, st>>>(P);
     else lists_large_kernel<LPL, IPL, SRC_FED_SEL, false><<<grid, 256, 0, st>>>(P);
+  } else if (src == SRC_PHILOX_TAB) {
+    lists_large_kernel<LPL, IPL, SRC_PHILOX_TAB, true><<<grid, 256, 0, st>>>(P);
   } else if (src == SRC_FED_RANK) {
     lists_large_kernel<LPL, IPL, SRC_FED_RANK, true><<<grid, 256, 0, st>>>(P);
   } else {

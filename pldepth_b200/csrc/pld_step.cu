@@ -15,6 +15,7 @@
 
 namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
+int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
@@ -379,7 +380,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   PLD_REQUIRE(ctx && mask && gt && pred && loss, "null argument");
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
   PLD_REQUIRE((long long)H * W <= PLD_MAX_PIXELS && (long long)Hm * Wm <= PLD_MAX_PIXELS, "map too large");
-  PLD_REQUIRE(K >= 1 && K <= 16, "pld_fused_step supports ranking_size 1..16 (use the staged calls above that)");
+  PLD_REQUIRE(K >= 1 && K <= PLD_MAX_RANKING_SIZE, "ranking_size must be in [1, 512]");
   PLD_REQUIRE(n >= 0 && (long long)B * n < (1ll << 31), "bad list count");
   PLD_REQUIRE((offset >> 48) == 0, "offset must fit in 48 bits");
   cudaStream_t st = (cudaStream_t)stream;
@@ -436,7 +437,8 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
     PLD_CUDA(cudaMemsetAsync(P.acc, 0, sizeof(long long) * gtotal, st));
   }
   ctx->time_begin(st);
-  rc = launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
+  rc = (K <= 16) ? launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st)
+                 : launch_lists_large(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   return rc;

@@ -78,7 +78,7 @@ class FusedPLStep(object):
                                             c_void_p(None), p(buf["grad"]), stream))
             self.step_index += 1
             return buf
-        if self.K <= 16:
+        if True:
             # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
             check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
                                      self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),

@@ -144,7 +144,8 @@ def test_fused_equals_sample_then_loss(cuda_device, K, n):
     assert g3 is None and r3 is None and l3.item() == loss.item()
 
 
-@pytest.mark.parametrize("K,n", [(1, 50), (2, 400), (5, 1500), (8, 700), (16, 300)])
+@pytest.mark.parametrize("K,n", [(1, 50), (2, 400), (5, 1500), (8, 700), (16, 300), (17, 90), (50, 150), (200, 30),
+                                 (512, 9)])
 @pytest.mark.parametrize("geometry", ["full", "holes", "scaled"])
 def test_one_call_step_equals_staged_calls(cuda_device, K, n, geometry):
     """pld_fused_step (lookup tables + fused kernel) == pld_mask_compact + pld_fused_sample_loss_bwd:

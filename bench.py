@@ -251,6 +251,8 @@ def run_b200(args):
 
     graphs = None
     if args.graph and world == 1:
+        from pldepth_b200._lib import Context as _Ctx
+        _Ctx.current(local_rank).device_offset(True, step.step_index)   # fresh draws on every replay
         graphs = []
         for s in range(n_sets):
             g = torch.cuda.CUDAGraph()

@@ -78,6 +78,12 @@ int pld_ctx_status(pld_ctx* ctx, void* stream, int* status_host);
  * extra 8 B/pixel scratch, a memset and a conversion pass. */
 int pld_ctx_set_deterministic(pld_ctx* ctx, int on);
 
+/* Device-resident Philox offset (off by default).  When enabled, every Philox entry point ignores its by-value
+ * `offset` argument, reads the offset from a counter in device memory instead (set to `start` here) and
+ * advances it by one at the end of the call.  The whole step then has no per-step host arguments, so it can be
+ * captured once in a CUDA graph and replayed with fresh random numbers each time.  (This call synchronises.) */
+int pld_ctx_device_offset(pld_ctx* ctx, int enable, uint64_t start);
+
 /* Measurement hook: with slots > 0 the library records a CUDA event pair on the launch stream
  * around every list-kernel launch (the dominant kernel of each entry point below) into a ring of
  * `slots` pairs; pld_ctx_kernel_times waits for them, returns the durations in ms and resets the

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pld_ctx_destroy": (c_int, [c_void_p]),
     "pld_ctx_status": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "pld_ctx_set_deterministic": (c_int, [c_void_p, c_int]),
+    "pld_ctx_device_offset": (c_int, [c_void_p, c_int, c_u64]),
     "pld_ctx_kernel_timing": (c_int, [c_void_p, c_int]),
     "pld_ctx_kernel_times": (c_int, [c_void_p, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_int)]),
     "pld_mask_compact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -139,6 +140,11 @@ class Context(object):
     def set_deterministic(self, on=True):
         """Bit-reproducible gradients (64-bit fixed-point accumulation) for this context."""
         check(self.lib.pld_ctx_set_deterministic(self.handle, 1 if on else 0))
+
+    def device_offset(self, enable=True, start=0):
+        """Keep the Philox offset in device memory (advanced by the library after every step): makes the
+        step capturable in a CUDA graph."""
+        check(self.lib.pld_ctx_device_offset(self.handle, 1 if enable else 0, int(start)))
 
     def kernel_timing(self, slots):
         check(self.lib.pld_ctx_kernel_timing(self.handle, int(slots)))

@@ -5,6 +5,7 @@ namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
+int launch_offset_advance(pld_ctx* ctx, cudaStream_t st);
 int mt_compact_images(pld_ctx* ctx, const int32_t* n_valid, int B, int need_per_image, const uint32_t* raw,
                       int64_t n_raw, int64_t* consumed_io, int32_t* sel_out, cudaStream_t st);
 
@@ -39,12 +40,15 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
     }
     return PLD_OK;
   }
+  const bool dev_off = ctx->use_device_offset && src == SRC_PHILOX;
+  if (dev_off) P.offset_dev = ctx->d_offset;
   ctx->time_begin(st);
   int rc = (P.K <= 16) ? launch_lists_small(P, src, loss, ctx->num_sms, st)
                        : launch_lists_large(P, src, loss, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr)
     rc = launch_acc_finalize(ctx, P.grad, (size_t)P.B * (size_t)P.HW, P.scale, accumulate, st);
+  if (rc == PLD_OK && dev_off) rc = launch_offset_advance(ctx, st);
   return rc;
 }
 

@@ -64,6 +64,8 @@ struct pld_ctx {
   long long* d_acc;
   size_t acc_cap;
   int ensure_acc(size_t elems);
+  unsigned long long* d_offset;  // device-resident Philox offset counter (pld_ctx_device_offset)
+  int use_device_offset;
   int ensure_scratch(size_t bytes);
   int ensure_partials(int n);
   inline void time_begin(cudaStream_t st) { if (ev_cap > 0 && ev_count < ev_cap) cudaEventRecord(ev_start[ev_count], st); }

@@ -33,11 +33,23 @@ struct ListParams {
   int* status;
   int B, HW, valid_stride, n, K;
   uint32_t seed_lo, seed_hi, off_lo, off_hi16;
+  const unsigned long long* offset_dev;  // when set, the Philox offset is read from device memory (graph replay)
   int image_base;
   float scale;
 };
 
 #define PLD_LOG_EPS (-23.025850929940457f) /* float32(log(1e-10)), TF-Ranking _EPSILON */
+
+// Philox offset of this launch: by value, or from the context's device counter (CUDA-graph friendly)
+__device__ __forceinline__ void launch_offset(const ListParams& P, uint32_t& off_lo, uint32_t& off_hi16) {
+  off_lo = P.off_lo;
+  off_hi16 = P.off_hi16;
+  if (P.offset_dev != nullptr) {
+    const unsigned long long o = *P.offset_dev;
+    off_lo = (uint32_t)o;
+    off_hi16 = (uint32_t)((o >> 32) & 0xFFFFull) << 16;
+  }
+}
 
 // fire-and-forget float add into the dense gradient map (RED, no return value)
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {

@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
   const float* __restrict__ pred = P.pred + map_off;
   float local = 0.f;
   int bad = 0;
+  uint32_t off_lo, off_hi16;
+  launch_offset(P, off_lo, off_hi16);
 
   uint32_t M = 1, thresh = 0;
   bool identity = false;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
         }
       } else {
         uint32_t khi[IPL], klo[IPL], nopay[IPL];
-        const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16,
+        const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), off_lo, off_hi16,
                             P.seed_lo, P.seed_hi};
         int sel[IPL];
 #pragma unroll

@@ -6,9 +6,9 @@ namespace pld {
 
 // K Philox draws of list l of image (image_base + b), mapped to [0, M)
 template <int K>
-__device__ __forceinline__ void draw_philox(const ListParams& P, int b, int l, uint32_t M, uint32_t thresh,
-                                            int (&sel)[K]) {
-  const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), P.off_lo, P.off_hi16, P.seed_lo, P.seed_hi};
+__device__ __forceinline__ void draw_philox(const ListParams& P, uint32_t off_lo, uint32_t off_hi16, int b, int l,
+                                            uint32_t M, uint32_t thresh, int (&sel)[K]) {
+  const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), off_lo, off_hi16, P.seed_lo, P.seed_hi};
   bool rej = false;
 #pragma unroll
   for (int q = 0; q < (K + 3) / 4; ++q) {
@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
   const float* __restrict__ pred = P.pred + map_off;
   float local = 0.f;
   int bad = 0;
+  uint32_t off_lo, off_hi16;
+  launch_offset(P, off_lo, off_hi16);
 
   uint32_t M = 1, thresh = 0;
   bool identity = false;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     tab = P.table + (size_t)b * P.table_stride;
     const int l0 = blockIdx.x * 256 + threadIdx.x;
     if (blockIdx.x * 256 < P.n) {
-      draw_philox<K>(P, b, philox_list(l0 < P.n ? l0 : P.n - 1), M, thresh, pre_sel);
+      draw_philox<K>(P, off_lo, off_hi16, b, philox_list(l0 < P.n ? l0 : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
       for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
     }
@@ -142,12 +144,12 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           const int nbase = base + gridDim.x * 256;
           if (nbase < P.n) {
             const int ln = nbase + threadIdx.x;
-            draw_philox<K>(P, b, philox_list(ln < P.n ? ln : P.n - 1), M, thresh, pre_sel);
+            draw_philox<K>(P, off_lo, off_hi16, b, philox_list(ln < P.n ? ln : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
             for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
           }
         } else if (SRC == SRC_PHILOX) {
-          draw_philox<K>(P, b, active ? l : P.n - 1, M, thresh, sel);
+          draw_philox<K>(P, off_lo, off_hi16, b, active ? l : P.n - 1, M, thresh, sel);
         } else {
           const int32_t* __restrict__ sin = P.sel_in + list_id * K;
 #pragma unroll

@@ -390,6 +390,12 @@ __global__ void __launch_bounds__(MTC_THREADS) mt_scatter_kernel(
 }
 
 __global__ void copy_i64_kernel(const long long* src, long long* dst) { *dst = *src; }
+__global__ void offset_advance_kernel(unsigned long long* counter) { *counter += 1ull; }
+int launch_offset_advance(pld_ctx* ctx, cudaStream_t st) {
+  offset_advance_kernel<<<1, 1, 0, st>>>(ctx->d_offset);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
 
 // deterministic mode: fixed-point accumulators -> float gradient (grad = [grad +] acc * 2^-32 * scale)
 __global__ void __launch_bounds__(256) acc_finalize_kernel(const long long* __restrict__ acc, float* __restrict__ grad,
@@ -534,8 +540,21 @@ int pld_ctx_destroy(pld_ctx* ctx) {
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_acc);
+  cudaFree(ctx->d_offset);
   pld_ctx_kernel_timing(ctx, 0);
   delete ctx;
+  return PLD_OK;
+}
+
+int pld_ctx_device_offset(pld_ctx* ctx, int enable, uint64_t start) {
+  PLD_REQUIRE(ctx != nullptr, "null context");
+  PLD_REQUIRE((start >> 48) == 0, "offset must fit in 48 bits");
+  if (enable) {
+    if (!ctx->d_offset) PLD_CUDA(cudaMalloc(&ctx->d_offset, sizeof(unsigned long long)));
+    unsigned long long v = start;
+    PLD_CUDA(cudaMemcpy(ctx->d_offset, &v, sizeof(v), cudaMemcpyHostToDevice));
+  }
+  ctx->use_device_offset = enable ? 1 : 0;
   return PLD_OK;
 }
 

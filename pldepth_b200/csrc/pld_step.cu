@@ -17,6 +17,7 @@ namespace pld {
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st);
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
+int launch_offset_advance(pld_ctx* ctx, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
@@ -430,6 +431,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
+  if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
   if (grad != nullptr && ctx->deterministic) {
     rc = ctx->ensure_acc(gtotal);
     if (rc) return rc;
@@ -441,6 +443,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
                  : launch_lists_large(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
+  if (rc == PLD_OK && ctx->use_device_offset) rc = launch_offset_advance(ctx, st);
   return rc;
 }
 
@@ -543,6 +546,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
+  if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
   P.score_keys = keys;
   P.score_cfg = make_score_cfg(minmax, strategy, threshold, equality_penalty, promotion);
   rc = launch_lists_small_score(P, ctx->num_sms, st);
@@ -593,5 +597,6 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   rc = launch_lists_small(P, SRC_PHILOX_TAB, do_loss, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
+  if (rc == PLD_OK && ctx->use_device_offset) rc = launch_offset_advance(ctx, st);
   return rc;
 }

@@ -96,6 +96,21 @@ class FusedPLStep(object):
         self.step_index += 1
         return buf
 
+    def capture(self, gt, mask, pred, out=None):
+        """Capture the step for these (static) tensors in a CUDA graph.  The Philox offset moves into device
+        memory (``pld_ctx_device_offset``), so every ``graph.replay()`` draws fresh lists; new data is fed by
+        copying into the same gt / mask / pred tensors.  Returns (graph, output buffers).  While a captured step
+        is in use, other Philox calls on this thread's context share (and advance) the same device counter."""
+        dev = gt.device
+        ctx = Context.current(dev.index or 0)
+        ctx.device_offset(True, self.step_index)
+        self.run(gt, mask, pred, out=out)                 # warm-up: scratch allocation happens outside capture
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            buf = self.run(gt, mask, pred, out=out)
+        return graph, buf
+
     @staticmethod
     def new_buffers(B, H, W, Hm, Wm, R, K, dev, emit_rankings=True):
         return dict(

@@ -352,3 +352,39 @@ def test_maximum_map_size(cuda_device):
     with pytest.raises(Exception):
         ops.fused_step(torch.ones((1, 4097, 2048), device=cuda_device), torch.rand((1, 4097, 2048), device=cuda_device),
                        torch.randn((1, 4097, 2048, 1), device=cuda_device), K, 10, seed=1)
+
+
+@pytest.mark.parametrize("strategy", ["purely", "thresholded"])
+def test_cuda_graph_replay_draws_fresh_lists(cuda_device, strategy):
+    """FusedPLStep.capture: the Philox offset lives on the device, so each replay equals the eager step with
+    the next offset (and differs from the previous replay)."""
+    from pldepth_b200 import ops
+    from pldepth_b200._lib import Context
+    from pldepth_b200.step import FusedPLStep
+    from tests.test_gpu_sampler import make_maps
+    B, H, W, K, R = 2, 32, 32, 5, 300
+    gt, mask = make_maps(H, W, H, W, 4, B)
+    pred = np.random.RandomState(1).randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    st = FusedPLStep(K, R, seed=6, strategy=strategy)
+    st.step_index = 10
+    ctx = Context.current(cuda_device.index or 0)
+    try:
+        graph, buf = st.capture(gt_d, mask_d, pred_d)         # warm-up consumed offset 10
+        seen = []
+        for i in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+            seen.append((buf["rankings"].clone(), buf["loss"].item()))
+        ctx.device_offset(False)
+        for i, (rank, loss) in enumerate(seen):
+            if strategy == "purely":
+                want = ops.fused_step(mask_d, gt_d, pred_d, K, R, seed=6, offset=11 + i)
+                wrank, wloss = want[3], want[0].item()
+            else:
+                want = ops.fused_step_scored(mask_d, gt_d, pred_d, K, int(R * 1.5), R, strategy, seed=6, offset=11 + i)
+                wrank, wloss = want["rankings"], want["loss"].item()
+            assert torch.equal(rank, wrank) and loss == wloss
+        assert not torch.equal(seen[0][0], seen[1][0])
+    finally:
+        ctx.device_offset(False)

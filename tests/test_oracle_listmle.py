@@ -10,6 +10,9 @@ from oracle import listmle_oracle as lo
 
 
 def test_plackett_luce_known_answer():
+    # Scores / labels of TF-Ranking's own published unit test (tensorflow_ranking/python/losses_test.py,
+    # test_list_mle_loss, as recalled -- the package cannot be fetched here): expected per-list NLL
+    # -(ln(3/6) + ln(2/3) + ln(1/1)) and -(ln(3/6) + ln(1/3) + ln(2/2)), mean 1.4451859.
     # P(order) = prod_i w_i / sum_{j>=i} w_j with w = exp(score)
     s = np.array([[0, np.log(3), np.log(2)], [0, np.log(2), np.log(3)]], np.float32)
     lab = np.array([[0, 2, 1], [1, 0, 2]], np.float32)

@@ -223,7 +223,6 @@ def run_b200(args):
                          pred=torch.from_numpy(np.roll(pred_h, s, axis=0)).to(dev),
                          out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev)))
     step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B)
-    loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
 
     pending = []
 
@@ -339,7 +338,6 @@ def run_b200(args):
     mask_p = torch.from_numpy(mask_h).pin_memory()
     pred_p = [torch.from_numpy(np.roll(pred_h, s, axis=0)).pin_memory() for s in range(2)]
     runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B)
-    red_buf = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def e2e_step(i):
         t = runner.submit(gt_p[i % 2], mask_p, pred_p[i % 2])

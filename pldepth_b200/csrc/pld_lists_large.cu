@@ -75,12 +75,6 @@ __device__ __forceinline__ float group_sum(float v) {
   for (int o = LPL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-template <int LPL>
-__device__ __forceinline__ bool group_all(bool v, int lane) {
-  const uint32_t bal = __ballot_sync(0xffffffffu, v);
-  const uint32_t gmask = (LPL == 32) ? 0xffffffffu : (((1u << LPL) - 1u) << (lane & ~(LPL - 1)));
-  return (bal & gmask) == gmask;
-}
 // sum of `v` over lanes of the group with a larger / smaller group-lane index
 template <int LPL>
 __device__ __forceinline__ float group_excl_suffix(float v, int gl) {
@@ -110,6 +104,7 @@ __device__ __forceinline__ float group_excl_prefix(float v, int gl) {
 #endif
 template <int LPL, int IPL, int SRC, bool LOSS>
 __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(const ListParams P) {
+  __shared__ uint32_t s_park[(SRC == SRC_PHILOX_TAB) ? IPL * 256 : 1];
   constexpr int GPW = 32 / LPL;    // groups per warp
   constexpr int GPB = 256 / LPL;   // groups per block
   const int K = P.K;
@@ -261,9 +256,19 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
               const bool on = (emask >> i) & 1u;
               khi[i] = on ? float_to_ordered(t[i].x) : 0u;
               klo[i] = on ? (((uint32_t)(gl * IPL + i) << 23) | (uint32_t)sel[i]) : 0u;
-              s_tab[i] = __float_as_uint(t[i].y);
+              // the prediction is parked in shared memory under its draw slot and fetched back by the slot id
+              // that survives in klo: 2 shared-memory ops per entry instead of a payload word in all 21+ stages
+              s_park[i * 256 + threadIdx.x] = __float_as_uint(t[i].y);
             }
-            bitonic_desc<LPL, IPL, true>(khi, klo, s_tab, gl);
+            bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < IPL; ++i) {
+              const uint32_t e = klo[i] >> 23;                       // original draw slot of this sorted entry
+              const int owner = (int)(threadIdx.x & ~(LPL - 1)) + (int)(e / IPL);
+              s_tab[i] = s_park[(e % IPL) * 256 + owner];
+            }
+            __syncwarp();
             have_s = true;
           } else {         // entry j = (bits of flat index p_j, gt[p_j])
 #pragma unroll

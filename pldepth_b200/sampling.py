@@ -119,9 +119,6 @@ class PurelyMaskedRandomSamplingStrategy(RandomSamplingStrategy):
     def determine_x_y_scales(image, mask):
         return image.shape[0] / mask.shape[0], image.shape[1] / mask.shape[1]
 
-    def _score_args(self):
-        return 0.03, -1000
-
     # ---- device-native batched API -------------------------------------------------------
     def draw_candidates(self, gt, mask, n, image_shape=None, image_base=0):
         """gt [B,H,W] / mask [B,Hm,Wm] device tensors -> candidate rankings [B,n,K,2] on the

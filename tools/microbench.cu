@@ -260,11 +260,6 @@ int main() {
   CK(cudaFuncSetAttribute(k_gather_smem<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_atomic_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid1 = g_sms;   // one 200 KB CTA per SM
-  for (int threads_mult = 1; threads_mult <= 4; threads_mult *= 2) {
-    // 256-thread CTAs, one per SM: vary resident warps by launching several waves is not possible
-    // with 200 KB smem, so report the single-CTA rate (8 warps/SM).
-    (void)threads_mult; break;
-  }
   const double ops1 = (double)grid1 * 256 * ITERS * UNR;
   timeit("gather_smem_4B_200KB_8warps", ops1, [&] { k_gather_smem<float><<<grid1, 256, smem>>>(smem / 4, out); });
   timeit("gather_smem_8B_200KB_8warps", ops1, [&] { k_gather_smem<float2><<<grid1, 256, smem>>>(smem / 8, out); });

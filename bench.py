@@ -128,16 +128,22 @@ def _cpu_image_job(job):
 
 
 def cpu_rate_single(shape, seconds):
-    """cpu_baseline: one core, bounded sample (one image, enough lists for ~`seconds`)."""
-    H, W, K = shape["H"], shape["W"], shape["K"]
+    """cpu_baseline: one core, bounded sample of the same workload (whole images of R lists until about
+    `seconds` of CPU work are done)."""
+    H, W, K, R = shape["H"], shape["W"], shape["K"], shape["R"]
     probe = _cpu_image_job((H, W, K, 2000, 123))
     per_list = (probe[1] + probe[2]) / probe[0]
-    lists = int(max(2000, min(shape["R"], seconds / per_list)))
-    n, ts, tl = _cpu_image_job((H, W, K, lists, 124))
+    lists_total = int(max(2000, seconds / per_list))
+    per_image = min(R, lists_total)
+    n_img = max(1, min(shape["B"], int(round(lists_total / per_image))))
+    n = ts = tl = 0.0
+    for i in range(n_img):
+        a, b_, c = _cpu_image_job((H, W, K, per_image, 124 + i))
+        n, ts, tl = n + a, ts + b_, tl + c
     return {"value": n / (ts + tl), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "1 image %dx%d, K=%d, %d lists: sampler loop %.2fs + ListMLE fwd+bwd (NumPy fp32) %.2fs; "
+            "sample": "%d image(s) %dx%d, K=%d, %d lists each: sampler loop %.2fs + ListMLE fwd+bwd (NumPy fp32) %.2fs; "
                       "the reference's sampler is a GIL-bound Python loop, so 1 core is its real rate per "
-                      "tf.data worker" % (H, W, K, n, ts, tl),
+                      "tf.data worker" % (n_img, H, W, K, per_image, ts, tl),
             "sampler_lists_per_s": n / ts, "loss_lists_per_s": n / tl}
 
 

@@ -60,6 +60,10 @@ CASES = [
     ("information_k5", "InformationScoreBasedSampling", 24, 32, 24, 32, 5, 30, None, 18, "ladder", True),
     ("information_k12", "InformationScoreBasedSampling", 24, 32, 24, 32, 12, 20, None, 19, "perm", False),
     ("information_k3_full", "InformationScoreBasedSampling", 16, 16, 16, 16, 3, 25, None, 20, "perm", False),
+    # long lists (group-per-list kernels, NumPy pairwise summation beyond 8 / 128 terms)
+    ("purely_k50", "PurelyMaskedRandomSamplingStrategy", 40, 48, 40, 48, 50, 20, 1.0, 21, "perm", True),
+    ("thresholded_k33", "ThresholdedMaskedRandomSamplingStrategy", 40, 48, 40, 48, 33, 16, None, 22, "perm", True),
+    ("information_k130", "InformationScoreBasedSampling", 40, 48, 40, 48, 130, 6, None, 23, "perm", False),
 ]
 
 
@@ -85,6 +89,16 @@ def main():
             used_factor = float(factor)
         st1 = np.random.get_state()
         consumed = words_consumed(st0, st1, 200000)
+        if cls != "PurelyMaskedRandomSamplingStrategy":
+            # a golden is only a pin if the reference's (unstable) argsort had no tied scores to break
+            from oracle import sampler_oracle as so
+            strat_name = {"MaskedRandomSamplingStrategy": "masked", "ThresholdedMaskedRandomSamplingStrategy": "thresholded",
+                          "InformationScoreBasedSampling": "information"}[cls]
+            _, _, scores = so.sample_masked_point_batch(strat_name, (H, W), mask, gt, R, K, factor,
+                                                        rng=np.random.RandomState(seed))
+            if np.unique(scores).size != scores.size:
+                print("  note: %s has tied candidate scores (sum of adjacent differences telescopes to max - min); "
+                      "the reference's unstable argsort may order them either way" % name)
         np.savez_compressed(os.path.join(OUT, "sampler_%s.npz" % name), gt=gt, mask=mask, seed=seed, K=K, R=R,
                             factor=used_factor, strategy=cls, rankings=np.asarray(out, dtype=np.float32),
                             consumed=consumed, numpy_version=np.__version__)

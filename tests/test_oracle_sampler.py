@@ -32,7 +32,7 @@ def oracle_run(c, rng):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 10
+    assert len(GOLDEN) >= 13
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[8:-4] for p in GOLDEN])

@@ -184,6 +184,13 @@ int pld_fused_sample_loss_bwd(pld_ctx* ctx, const float* gt, const int32_t* vali
                               double* loss_sum, float* per_list, float* grad, int accumulate,
                               void* stream);
 
+/* Stage 2 alone: prepare_fully_fledged_loss_input (depth_utils.py:39-61) -- selected[b*R*K + t] =
+ * pred[b][int32(rankings[b][t].index)], labels = rankings[...].depth; both shaped [B*R, K].
+ * labels may be NULL.  (The fused kernels do this gather in registers; this entry point exists for callers
+ * that want the reference's intermediate tensors.) */
+int pld_gather_predictions(pld_ctx* ctx, const float* rankings, const float* pred, int B, int R, int K, int HW,
+                           float* selected, float* labels, void* stream);
+
 /* ---- whole step in one call: stages 1a + 1b + 2 + 3 -------------------------------------------
  * What one training step of the reference does between the data pipeline and the decoder's
  * backward: np.where(mask) (sampling.py:135) + sample_masked_rankings (sampling.py:131-145, n == R

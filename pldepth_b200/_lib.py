@@ -59,6 +59,8 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_double, c_double, c_int, c_u64, c_u64, c_int, c_float,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
+    "pld_gather_predictions": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
     "pld_ordinal_error": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
     "pld_ndcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -114,6 +114,24 @@ __global__ void __launch_bounds__(256) ndcg_kernel(const float* __restrict__ op,
   if (bad) atomicOr(status, bad);
 }
 
+// prepare_fully_fledged_loss_input (depth_utils.py:39-61) as a standalone op: batched gather of the
+// predictions at the flat indices of the rankings + de-interleaved labels.
+__global__ void __launch_bounds__(256) gather_predictions_kernel(const float2* __restrict__ rankings,
+                                                                const float* __restrict__ pred, size_t per_image,
+                                                                int HW, size_t total, float* __restrict__ selected,
+                                                                float* __restrict__ labels, int* status) {
+  int bad = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const float2 v = __ldg(rankings + i);
+    const size_t b = i / per_image;
+    int q = (int)v.x;
+    if (q < 0 || q >= HW) { bad = PLD_ST_BAD_INDEX; q = 0; }
+    selected[i] = __ldg(pred + b * (size_t)HW + q);
+    if (labels != nullptr) labels[i] = v.y;
+  }
+  if (bad) atomicOr(status, bad);
+}
+
 }  // namespace pld
 
 using namespace pld;
@@ -125,6 +143,20 @@ int pld_ordinal_error(pld_ctx* ctx, const float* pred, const float* gt, const in
   PLD_REQUIRE(ctx && pred && gt && idx0 && idx1 && err, "null argument");
   PLD_REQUIRE(N > 0 && HW > 0 && num > 0, "bad shape");
   ordinal_error_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(pred, gt, idx0, idx1, HW, num, err, ctx->d_status);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+int pld_gather_predictions(pld_ctx* ctx, const float* rankings, const float* pred, int B, int R, int K, int HW,
+                           float* selected, float* labels, void* stream) {
+  PLD_REQUIRE(ctx && rankings && pred && selected, "null argument");
+  PLD_REQUIRE(B > 0 && R >= 0 && K >= 1 && HW > 0, "bad shape");
+  const size_t per_image = (size_t)R * K, total = per_image * B;
+  if (total == 0) return PLD_OK;
+  int gx = (int)((total + 255) / 256);
+  if (gx > ctx->num_sms * 16) gx = ctx->num_sms * 16;
+  gather_predictions_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(rankings), pred,
+                                                                  per_image, HW, total, selected, labels, ctx->d_status);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

@@ -94,3 +94,39 @@ class HourglassNegativeLogLikelihood(object):
     def get_config(self):
         return {"ranking_size": self.ranking_size, "batch_size": self.batch_size, "reduction": self.reduction,
                 "name": self.name}
+
+
+class NegativeLogLikelihoodLoss(object):
+    """Drop-in for pldepth/losses/nll_loss.py:10-29 (``NegativeLogLikelihoodLoss`` -> ``MetaBatchListMLELoss``):
+    labels and logits arrive already gathered, any shape that reshapes to ``[-1, ranking_size]``.  Runs on the
+    same kernel by viewing the logits as one flat map indexed 0..L*K-1 (chunked below 2^23 entries)."""
+
+    def __init__(self, ranking_size, reduction="auto", name=None, lambda_weight=None):
+        red = str(getattr(reduction, "name", reduction)).lower()
+        if red not in ("auto", "sum_over_batch_size", "sum"):
+            raise ValueError("unsupported reduction %r" % (reduction,))
+        if lambda_weight is not None:
+            raise NotImplementedError("lambda_weight is not used anywhere in the reference; only None is supported")
+        self.ranking_size, self.reduction, self.name = int(ranking_size), red, name
+
+    def __call__(self, y_true, y_pred, sample_weight=None):
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is never passed by the reference")
+        K = self.ranking_size
+        labels = y_true.reshape(-1, K).to(torch.float32)
+        logits = y_pred.reshape(-1, K)
+        L = labels.shape[0]
+        scale = 1.0 / L if self.reduction != "sum" else 1.0
+        chunk = max(1, (1 << 23) // K)
+        total = None
+        for lo in range(0, L, chunk):
+            hi = min(L, lo + chunk)
+            n = hi - lo
+            idx = torch.arange(n * K, device=labels.device, dtype=torch.float32).reshape(n, K)
+            y = torch.stack([idx, labels[lo:hi]], dim=-1).reshape(1, n, K, 2)
+            part = _ListMLEFunction.apply(logits[lo:hi].reshape(1, n * K), y, 1, K, "sum", None) * scale
+            total = part if total is None else total + part
+        return total
+
+
+MetaBatchListMLELoss = NegativeLogLikelihoodLoss

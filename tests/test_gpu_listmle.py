@@ -388,3 +388,25 @@ def test_cuda_graph_replay_draws_fresh_lists(cuda_device, strategy):
         assert not torch.equal(seen[0][0], seen[1][0])
     finally:
         ctx.device_offset(False)
+
+
+def test_pre_gathered_loss_and_standalone_gather(cuda_device):
+    """NegativeLogLikelihoodLoss (nll_loss.py:10-29) and prepare_fully_fledged_loss_input (depth_utils.py:39-61)."""
+    from pldepth_b200.depth_utils import get_depth_relation, prepare_fully_fledged_loss_input
+    from pldepth_b200.losses import NegativeLogLikelihoodLoss
+    B, H, W, K, R = 2, 16, 12, 6, 70
+    y_true, pred = make_problem(B, H, W, K, R, 4, sorted_lists=False)
+    yt, p = torch.from_numpy(y_true).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    sel, lab = prepare_fully_fledged_loss_input(yt, p, B, K)
+    idx, want_lab = lo.split_rankings(y_true, B, K)
+    want_sel = lo.gather_predictions(pred, idx, B, K)
+    assert np.array_equal(sel.cpu().numpy(), want_sel) and np.array_equal(lab.cpu().numpy(), want_lab)
+    logits = sel.clone().requires_grad_(True)
+    val = NegativeLogLikelihoodLoss(K)(lab, logits)
+    val.backward()
+    nll, g = lo.listmle_per_list(want_lab, want_sel)
+    assert_close(val.item(), nll.mean(), "pre-gathered loss")
+    assert_close(logits.grad.cpu().numpy(), g / nll.shape[0], "pre-gathered gradient")
+    assert get_depth_relation(1.0, 0.5) == 1 and get_depth_relation(0.5, 1.0) == -1 and get_depth_relation(2, 2) == 0
+    assert get_depth_relation(1.02, 1.0, 0.03) == 0 and get_depth_relation(1.04, 1.0, 0.03) == 1
+    assert get_depth_relation(1.0, 1.04, 0.03) == -1

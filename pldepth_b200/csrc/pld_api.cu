@@ -10,6 +10,7 @@ int mt_compact_images(pld_ctx* ctx, const int32_t* n_valid, int B, int need_per_
                       int64_t n_raw, int64_t* consumed_io, int32_t* sel_out, cudaStream_t st);
 
 static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumulate, cudaStream_t st) {
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(P.B > 0 && P.B <= 65535, "B out of range");
   PLD_REQUIRE(P.n >= 0, "negative list count");
   PLD_REQUIRE(P.K >= 1 && P.K <= PLD_MAX_RANKING_SIZE, "ranking_size must be in [1, 512]");
@@ -34,6 +35,8 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
     }
   }
   if (P.n == 0) {
+    if (loss && P.grad != nullptr && P.acc != nullptr && !accumulate)   // deterministic mode: nothing to convert
+      PLD_CUDA(cudaMemsetAsync(P.grad, 0, sizeof(float) * (size_t)P.B * (size_t)P.HW, st));
     if (loss) {
       if (P.loss) PLD_CUDA(cudaMemsetAsync(P.loss, 0, sizeof(float), st));
       if (P.loss_sum) PLD_CUDA(cudaMemsetAsync(P.loss_sum, 0, sizeof(double), st));

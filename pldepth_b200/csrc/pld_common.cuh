@@ -34,6 +34,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     }                                                    \
   } while (0)
 
+// every entry point runs on the context's device: refuse a call made while another device is current
+#define PLD_CHECK_DEVICE(ctx)                                                                             \
+  do {                                                                                                    \
+    int dev__ = -1;                                                                                       \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ != (ctx)->device) {                                 \
+      pld::set_error("context was created on device %d but device %d is current", (ctx)->device, dev__);  \
+      return PLD_EINVAL;                                                                                  \
+    }                                                                                                     \
+  } while (0)
+
 #define PLD_CHECK_LAUNCH()                                                                  \
   do {                                                                                     \
     pld::count_launch();                                                                   \

@@ -141,6 +141,7 @@ extern "C" {
 int pld_ordinal_error(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* idx0, const int32_t* idx1,
                       int N, int HW, int num, float* err, void* stream) {
   PLD_REQUIRE(ctx && pred && gt && idx0 && idx1 && err, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(N > 0 && HW > 0 && num > 0, "bad shape");
   ordinal_error_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(pred, gt, idx0, idx1, HW, num, err, ctx->d_status);
   PLD_CHECK_LAUNCH();
@@ -150,6 +151,7 @@ int pld_ordinal_error(pld_ctx* ctx, const float* pred, const float* gt, const in
 int pld_gather_predictions(pld_ctx* ctx, const float* rankings, const float* pred, int B, int R, int K, int HW,
                            float* selected, float* labels, void* stream) {
   PLD_REQUIRE(ctx && rankings && pred && selected, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && R >= 0 && K >= 1 && HW > 0, "bad shape");
   const size_t per_image = (size_t)R * K, total = per_image * B;
   if (total == 0) return PLD_OK;
@@ -164,6 +166,7 @@ int pld_gather_predictions(pld_ctx* ctx, const float* rankings, const float* pre
 int pld_ndcg(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* ids, int N, int HW, int n, float* out,
              void* stream) {
   PLD_REQUIRE(ctx && pred && gt && ids && out, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(N > 0 && HW > 0 && n > 0 && n <= 1024, "list_size must be in [1, 1024]");
   int p2 = 1;
   while (p2 < n) p2 <<= 1;

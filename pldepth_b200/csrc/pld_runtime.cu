@@ -605,6 +605,7 @@ int pld_ctx_status(pld_ctx* ctx, void* stream, int* status_host) {
 int pld_mask_compact(pld_ctx* ctx, const float* mask, int B, int Hm, int Wm, int H, int W,
                      int32_t* valid_flat, int32_t* n_valid, void* stream) {
   PLD_REQUIRE(ctx && mask && valid_flat && n_valid, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
   PLD_REQUIRE((long long)H * W <= PLD_MAX_PIXELS, "H*W exceeds PLD_MAX_PIXELS");
   PLD_REQUIRE((long long)Hm * Wm <= PLD_MAX_PIXELS, "Hm*Wm exceeds PLD_MAX_PIXELS");
@@ -627,6 +628,7 @@ int pld_mask_compact(pld_ctx* ctx, const float* mask, int B, int Hm, int Wm, int
 
 int pld_mt19937_init(pld_ctx* ctx, uint32_t seed, uint32_t* state, int32_t* pos, void* stream) {
   PLD_REQUIRE(ctx && state && pos, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   mt_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(seed, state, pos);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
@@ -635,6 +637,7 @@ int pld_mt19937_init(pld_ctx* ctx, uint32_t seed, uint32_t* state, int32_t* pos,
 int pld_mt19937_generate(pld_ctx* ctx, uint32_t* state, int32_t* pos, uint32_t* out, int64_t n,
                          void* stream) {
   PLD_REQUIRE(ctx && state && pos && (out || n == 0), "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(n >= 0, "negative count");
   if (n == 0) return PLD_OK;
   mt_generate_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, pos, out, (long long)n);
@@ -644,6 +647,7 @@ int pld_mt19937_generate(pld_ctx* ctx, uint32_t* state, int32_t* pos, uint32_t* 
 
 int pld_gt_minmax(pld_ctx* ctx, const float* gt, int B, int HW, float* gt_minmax, void* stream) {
   PLD_REQUIRE(ctx && gt && gt_minmax, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && HW > 0, "bad shape");
   gt_minmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(gt, HW, gt_minmax);
   PLD_CHECK_LAUNCH();
@@ -654,6 +658,7 @@ int pld_score_lists(pld_ctx* ctx, const float* rankings, const float* gt_minmax,
                     int strategy, double threshold, double equality_penalty, int promotion,
                     double* scores, void* stream) {
   PLD_REQUIRE(ctx && rankings && scores, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && B <= 65535 && n > 0 && K >= 1 && K <= PLD_MAX_RANKING_SIZE, "bad shape");
   PLD_REQUIRE(strategy >= PLD_STRATEGY_MASKED && strategy <= PLD_STRATEGY_INFORMATION, "bad strategy");
   PLD_REQUIRE(strategy != PLD_STRATEGY_INFORMATION || gt_minmax != nullptr, "gt_minmax required");
@@ -674,6 +679,7 @@ int pld_score_lists(pld_ctx* ctx, const float* rankings, const float* gt_minmax,
 int pld_select_top(pld_ctx* ctx, const double* scores, const float* rankings, int B, int n, int K, int R,
                    float* rankings_out, int32_t* order_out, void* stream) {
   PLD_REQUIRE(ctx && scores && rankings && rankings_out, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && B <= 65535 && n > 0 && K >= 1 && R >= 0 && R <= n, "bad shape");
   PLD_REQUIRE((long long)B * n < (1ll << 31), "too many candidates");
   if (R == 0) return PLD_OK;

@@ -379,6 +379,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
                               float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
                               float* per_list, float* grad, void* stream) {
   PLD_REQUIRE(ctx && mask && gt && pred && loss, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
   PLD_REQUIRE((long long)H * W <= PLD_MAX_PIXELS && (long long)Hm * Wm <= PLD_MAX_PIXELS, "map too large");
   PLD_REQUIRE(K >= 1 && K <= PLD_MAX_RANKING_SIZE, "ranking_size must be in [1, 512]");
@@ -453,6 +454,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
                                      int image_base, float scale, int32_t* n_valid, int32_t* order_out, float* rankings,
                                      float* loss, double* loss_sum, float* per_list, float* grad, void* stream) {
   PLD_REQUIRE(ctx && mask && gt, "null argument");
+  PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(pred != nullptr || (loss == nullptr && grad == nullptr && per_list == nullptr), "pred is required for the loss");
   PLD_REQUIRE(rankings != nullptr || loss != nullptr, "no output requested");
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--R", type=int, default=100000)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--graph", action="store_true", help="replay each fused step from a CUDA graph (FusedPLStep.capture)")
     args = ap.parse_args()
     from pldepth_b200 import ops, sampling, synth
     from pldepth_b200._lib import Context
@@ -46,6 +47,11 @@ def main():
             return ops.fused_step_scored(mask, gt, pred, K, n, R, s._strategy, 0.03, -1000, "nep50", seed=1,
                                          offset=step.i)
         step.i = 0
+        if args.graph and not name.startswith("purely"):
+            from pldepth_b200.step import FusedPLStep
+            fs = FusedPLStep(K, R, seed=1, strategy=s._strategy)
+            graph, _ = fs.capture(gt, mask, pred)
+            step = graph.replay
         for _ in range(3):
             step()
         torch.cuda.synchronize()
@@ -58,7 +64,9 @@ def main():
         torch.cuda.synchronize()
         ms = a.elapsed_time(b_) / args.steps
         launches = (Context.current(0).lib.pld_launch_count() - l0) / args.steps
-        print(json.dumps({"strategy": name, "candidate_factor": s._default_factor if f is None else f,
+        if args.graph:
+            Context.current(0).device_offset(False)
+        print(json.dumps({"strategy": name, "cuda_graph": bool(args.graph and not name.startswith("purely")), "candidate_factor": s._default_factor if f is None else f,
                           "kept_lists_per_s": B * R / (ms * 1e-3), "ms_per_step": ms, "launches_per_step": launches,
                           "shape": "B=%d %dx%d K=%d R=%d" % (B, H, W, K, R)}))
 

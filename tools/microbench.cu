@@ -240,6 +240,8 @@ int main() {
   timeit("gather_global_4B_image_major_784KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION, NREG, out); });
   timeit("gather_global_8B_image_major_1.5MB", ops, [&] { k_gather_global<float2><<<grid, 256>>>((float2*)map, REGION, NREG, out); });
   timeit("gather_global_16B_image_major_3MB", ops, [&] { k_gather_global<float4><<<grid, 256>>>((float4*)map, REGION, NREG, out); });
+  timeit("gather_global_4B_L1_resident_64KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, 16384, NREG * 8, out); });
+  timeit("gather_global_8B_L1_resident_64KB", ops, [&] { k_gather_global<float2><<<grid, 256>>>((float2*)map, 8192, NREG * 8, out); });
   timeit("gather_global_4B_whole_25MB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION * NREG, 1, out); });
   timeit("red_global_f32_image_major_784KB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION, NREG); });
   timeit("red_global_f32_whole_25MB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION * NREG, 1); });

@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for cpu_baseline")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--no-emit", action="store_true", help="do not materialise the rankings (what a fused training "
+                                                           "step needs; the default emits them like the reference)")
     ap.add_argument("--hole", type=float, default=0.0, help="fraction of each mask zeroed (default: all-ones mask)")
     return ap.parse_args()
 
@@ -227,8 +229,8 @@ def run_b200(args):
         sets.append(dict(gt=torch.from_numpy(np.roll(gt_h, s, axis=0)).to(dev),
                          mask=torch.from_numpy(mask_h).to(dev),
                          pred=torch.from_numpy(np.roll(pred_h, s, axis=0)).to(dev),
-                         out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev)))
-    step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B)
+                         out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev, emit_rankings=not args.no_emit)))
+    step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B, emit_rankings=not args.no_emit)
 
     pending = []
 
@@ -343,7 +345,8 @@ def run_b200(args):
     gt_p = [torch.from_numpy(np.roll(gt_h, s, axis=0)).pin_memory() for s in range(2)]
     mask_p = torch.from_numpy(mask_h).pin_memory()
     pred_p = [torch.from_numpy(np.roll(pred_h, s, axis=0)).pin_memory() for s in range(2)]
-    runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B)
+    runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B,
+                               emit_rankings=not args.no_emit)
 
     def e2e_step(i):
         t = runner.submit(gt_p[i % 2], mask_p, pred_p[i % 2])
@@ -381,9 +384,10 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s per GPU: B=%d images %dx%d, ranking_size K=%d, R=%d lists/image, %s "
-                                   "mask, core sampler (factor 1.0), rankings emitted" % (
+                                   "mask, core sampler (factor 1.0), rankings %s" % (
                                        args.workload, B, H, W, K, R,
-                                       "all-ones" if args.hole == 0 else "%.0f%%-hole" % (100 * args.hole)),
+                                       "all-ones" if args.hole == 0 else "%.0f%%-hole" % (100 * args.hole),
+                                       "not materialised" if args.no_emit else "emitted"),
                        "lists_per_step": L * world, "sharding": "per image, %d GPU(s)" % world,
                        "cache": "rotating %d input/output buffer sets of %.0f MB each (> 126 MB L2), no reuse "
                                 "between consecutive steps" % (n_sets, abytes / 1e6),

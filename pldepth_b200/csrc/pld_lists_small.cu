@@ -41,7 +41,7 @@ template <int K, int SRC, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
-  __shared__ float2 s_stage[(SRC != SRC_FED_RANK) ? 8 * 32 * STRIDE : 1];
+  __shared__ float2 s_stage[8 * 32 * STRIDE];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t map_off = (size_t)b * (size_t)P.HW;
@@ -97,17 +97,40 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
       bool have_s = false;
 
       if (SRC == SRC_FED_RANK) {
-        const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) + list_id * K;
+        // the warp's 32 rows are contiguous in memory: read them as full 256-byte rows into the staging
+        // buffer, then every thread picks up its own list
+        float2* st = s_stage + wid * (32 * STRIDE);
+        {
+          const int warp_first = base + wid * 32;
+          int cnt = P.n - warp_first;
+          cnt = cnt > 32 ? 32 : cnt;
+          if (cnt > 0) {
+            const float2* __restrict__ rin = reinterpret_cast<const float2*>(P.rank_in) +
+                                             ((size_t)b * (size_t)P.n + (size_t)warp_first) * K;
+            const int total = cnt * K;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const int e = i * 32 + lane;
+              if (e < total) {
+                const int li = e / K, kk = e - li * K;
+                st[li * STRIDE + kk] = __ldg(rin + e);
+              }
+            }
+          }
+          __syncwarp();
+        }
         bool sorted = true, valid_all = true;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const float2 v = __ldg(rin + k);
+          // lanes past the end of the image compute on a dummy list (index 0, label 0); nothing of theirs is stored
+          const float2 v = active ? st[lane * STRIDE + k] : make_float2(0.f, 0.f);
           int q = (int)v.x;  // tf.cast(point_coords, int32): truncation (depth_utils.py:50)
           if (q < 0 || q >= P.HW) { bad |= PLD_ST_BAD_INDEX; q = 0; }
           p[k] = q;
           lab[k] = v.y;
           valid_all = valid_all && (v.y >= 0.f);
         }
+        __syncwarp();
 #pragma unroll
         for (int k = 1; k < K; ++k) sorted = sorted && (lab[k - 1] >= lab[k]);
         if (!(sorted && valid_all)) {

@@ -410,3 +410,36 @@ def test_pre_gathered_loss_and_standalone_gather(cuda_device):
     assert get_depth_relation(1.0, 0.5) == 1 and get_depth_relation(0.5, 1.0) == -1 and get_depth_relation(2, 2) == 0
     assert get_depth_relation(1.02, 1.0, 0.03) == 0 and get_depth_relation(1.04, 1.0, 0.03) == 1
     assert get_depth_relation(1.0, 1.04, 0.03) == -1
+
+
+@pytest.mark.parametrize("name,B,H,W,K,R", [("C3", 16, 448, 448, 50, 50000), ("C5-slice", 4, 1024, 768, 10, 1000000)])
+def test_full_size_config3_and_config5_properties(cuda_device, name, B, H, W, K, R):
+    """BASELINE config 3 at full size and 4 of the 32 images of one GPU's config-5 share: depth-descending
+    lists that reproduce gt at their indices, loss == mean per-list NLL, gradient sums to ~0, and a random
+    sample of lists reproduces the oracle's per-list NLL (long lists: reverse log-cumsum-exp of length 50)."""
+    from pldepth_b200 import ops, synth
+    rs = np.random.RandomState(1)
+    base = synth.depth_map(H, W, 3000 + K)
+    gt = np.stack([np.roll(base, 53 * b, axis=0) for b in range(B)])
+    pred = rs.standard_normal((B, H, W, 1)).astype(np.float32)
+    gt_d, pred_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    mask_d = torch.ones((B, H, W), device=cuda_device)
+    loss, loss_sum, grad, rank, per_list, nv = ops.fused_step(mask_d, gt_d, pred_d, K, R, seed=3, want_per_list=True)
+    ops.check_status(cuda_device)
+    d = rank[..., 1]
+    assert bool((d[:, :, :-1] >= d[:, :, 1:]).all())
+    idx = rank[..., 0].long()
+    assert int(idx.min()) >= 0 and int(idx.max()) < H * W
+    assert bool((torch.gather(gt_d.reshape(B, -1), 1, idx.reshape(B, -1)).reshape(B, R, K) == d).all())
+    assert abs(loss.item() - per_list.double().mean().item()) <= 2e-6 * abs(loss.item())
+    assert abs(loss_sum.item() - per_list.double().sum().item()) <= 2e-6 * abs(loss_sum.item())
+    gsum, gabs = grad.double().sum().item(), grad.double().abs().sum().item()
+    assert abs(gsum) <= 1e-5 * gabs
+    pick = rs.randint(0, R, size=1500)
+    b = B - 1
+    _, _, want_pl = lo.hourglass_nll(rank[b, pick].cpu().numpy()[None], pred[b:b + 1], 1, K)
+    assert_close(per_list.reshape(B, R)[b, pick].cpu().numpy(), want_pl, "%s per-list NLL at full size" % name)
+    # uniform draws: every image's index histogram over 64 equal bands is flat within 6 sigma
+    hist = torch.bincount((idx[b].reshape(-1) * 64) // (H * W), minlength=64).double()
+    exp = R * K / 64.0
+    assert float(((hist - exp).abs() / exp ** 0.5).max()) < 6.0

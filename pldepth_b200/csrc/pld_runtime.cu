@@ -507,19 +507,11 @@ int pld_version(void) { return 100; }
 const char* pld_last_error(void) { return pld::last_error(); }
 uint64_t pld_launch_count(void) { return pld::g_launches.load(); }
 
-int pld_ctx_create(int device, pld_ctx** out) {
-  PLD_REQUIRE(out != nullptr, "out is null");
-  int ndev = 0;
-  PLD_CUDA(cudaGetDeviceCount(&ndev));
-  PLD_REQUIRE(device >= 0 && device < ndev, "device out of range");
-  PLD_CUDA(cudaSetDevice(device));
-  pld_ctx* c = new (std::nothrow) pld_ctx();
-  if (!c) { set_error("out of host memory"); return PLD_ENOMEM; }
-  memset(c, 0, sizeof(*c));
+static int ctx_init(pld_ctx* c, int device) {
   c->device = device;
-  cudaDeviceProp prop;
-  PLD_CUDA(cudaGetDeviceProperties(&prop, device));
-  c->num_sms = prop.multiProcessorCount;
+  int num_sms = 0;
+  PLD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  c->num_sms = num_sms;
   PLD_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
   PLD_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
   PLD_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
@@ -527,12 +519,37 @@ int pld_ctx_create(int device, pld_ctx** out) {
   int rc = c->ensure_partials(4096);
   if (rc) return rc;
   PLD_CUDA(cudaDeviceSynchronize());
-  *out = c;
   return PLD_OK;
+}
+
+int pld_ctx_create(int device, pld_ctx** out) {
+  PLD_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  int ndev = 0, prev = 0;
+  PLD_CUDA(cudaGetDeviceCount(&ndev));
+  PLD_REQUIRE(device >= 0 && device < ndev, "device out of range");
+  PLD_CUDA(cudaGetDevice(&prev));
+  PLD_CUDA(cudaSetDevice(device));
+  pld_ctx* c = new (std::nothrow) pld_ctx();
+  if (!c) { set_error("out of host memory"); cudaSetDevice(prev); return PLD_ENOMEM; }
+  memset(c, 0, sizeof(*c));
+  const int rc = ctx_init(c, device);
+  if (rc != PLD_OK) {  // release whatever was allocated; the error message of the failing call is kept
+    cudaFree(c->d_status);
+    cudaFree(c->d_ticket);
+    cudaFree(c->d_partials);
+    delete c;
+  } else {
+    *out = c;
+  }
+  cudaSetDevice(prev);  // creating a context does not change the caller's current device
+  return rc;
 }
 
 int pld_ctx_destroy(pld_ctx* ctx) {
   if (!ctx) return PLD_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->d_status);
@@ -543,6 +560,7 @@ int pld_ctx_destroy(pld_ctx* ctx) {
   cudaFree(ctx->d_offset);
   pld_ctx_kernel_timing(ctx, 0);
   delete ctx;
+  cudaSetDevice(prev);
   return PLD_OK;
 }
 

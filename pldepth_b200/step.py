@@ -58,6 +58,12 @@ class FusedPLStep(object):
         """gt f32[B,H,W], mask f32[B,Hm,Wm], pred f32[B,H,W(,1)] on one CUDA device.
         Returns dict(loss f32[1], loss_sum f64[1], grad f32[B,H,W,1], rankings f32[B,R,K,2]|None).
         ``loss`` carries the factor 1/(global_batch*R) (global_batch defaults to B)."""
+        if torch.cuda.current_device() != (gt.device.index or 0):
+            with torch.cuda.device(gt.device):
+                return self._run(gt, mask, pred, out)
+        return self._run(gt, mask, pred, out)
+
+    def _run(self, gt, mask, pred, out=None):
         dev = gt.device
         B, H, W = gt.shape[0], gt.shape[1], gt.shape[2]
         Hm, Wm = mask.shape[1], mask.shape[2]

@@ -95,6 +95,37 @@ __global__ void __launch_bounds__(256) k_gather_then_red(const float* __restrict
   }
 }
 
+// scattered reductions through the bulk-copy (TMA) engine instead of the LSU: one 16-byte
+// cp.reduce.async.bulk per point (value in one of the four lanes, zeros elsewhere)
+template <bool MIXED>
+__global__ void __launch_bounds__(256) k_red_tma(float* __restrict__ map, uint32_t region_elems, uint32_t n_regions) {
+  __shared__ alignas(16) float stage[256 * 4];
+  float* base = map + (size_t)(blockIdx.x % n_regions) * region_elems;
+  stage[threadIdx.x * 4 + 0] = 1.0f;
+  stage[threadIdx.x * 4 + 1] = 0.f;
+  stage[threadIdx.x * 4 + 2] = 0.f;
+  stage[threadIdx.x * 4 + 3] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage + threadIdx.x * 4);
+  uint32_t s = (blockIdx.x * 256 + threadIdx.x) * 2654435761u + 777u;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float* dst = base + (__umulhi(xs32(s), region_elems / 4) * 4);
+      if (MIXED && (u & 1)) {
+        atomicAdd(dst, 1.0f);
+      } else {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 16;"
+                     ::"l"(dst), "r"(saddr) : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- shared memory --------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_smem(uint32_t elems, float* out) {
@@ -254,6 +285,8 @@ int main() {
     timeit("gather_tex1Dfetch_4B_image_major", ops, [&] { k_gather_tex<<<grid, 256>>>(tex, REGION, NREG, out); });
     timeit("gather_mixed_tex+ldg_4B_image_major", ops, [&] { k_gather_mixed<<<grid, 256>>>(tex, map, REGION, NREG, out); });
     timeit("scatter_store_8B_image_major", ops, [&] { k_scatter_store8<<<grid, 256>>>((float2*)map, REGION, NREG); });
+    timeit("red_tma_bulk16B_image_major", ops, [&] { k_red_tma<false><<<grid, 256>>>(map, REGION, NREG); });
+    timeit("red_mixed_tma+lsu_image_major", ops, [&] { k_red_tma<true><<<grid, 256>>>(map, REGION, NREG); });
     timeit("gather4B_then_red_pairs(ops=pairs)", ops, [&] { k_gather_then_red<<<grid, 256>>>(map, map + (size_t)REGION * NREG, REGION, NREG); });
   }
   const int smem = 200 * 1024;

@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           const double sc = (P.score_cfg.promotion == PLD_PROMOTION_NEP50)
                                 ? score_regs<float, K>(lab, P.score_cfg, b)
                                 : score_regs<double, K>(lab, P.score_cfg, b);
-          if (active) P.score_keys[list_id] = score_key(sc);
+          const bool f32_exact = P.score_cfg.promotion == PLD_PROMOTION_NEP50 &&
+                                 P.score_cfg.strategy != PLD_STRATEGY_INFORMATION;
+          if (active) P.score_keys[list_id] = f32_exact ? score_key_f32((float)sc) : score_key(sc);
           continue;
         }
         if (P.rank_out != nullptr) {

@@ -195,5 +195,14 @@ __device__ __forceinline__ uint64_t score_key(double s) {
   if (s == 0.0) s = 0.0;
   return double_to_ordered(s);
 }
+// Scores of the masked / thresholded strategies under NEP-50 promotion are float32 values stored in a float64
+// array: their order is carried by 32 bits.  Placing those in the HIGH word leaves the low four key bytes
+// constant, so the radix sort skips four of its eight passes and the 36-bit selection prefix is exact.
+__device__ __forceinline__ uint64_t score_key_f32(float s) {
+  if (s == 0.f) s = 0.f;
+  uint32_t u = __float_as_uint(s);
+  u ^= ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+  return (uint64_t)u << 32;
+}
 
 }  // namespace pld

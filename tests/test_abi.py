@@ -56,3 +56,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_header_is_valid_c_and_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and a plain-C program must link against the
+    library and call it (no GPU needed for pld_version / pld_last_error)."""
+    import shutil
+    import subprocess
+    from pldepth_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "pldepth_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { pld_ctx* c = 0; (void)c; printf("%d %s", pld_version(), pld_last_error()); '
+                   'return pld_ctx_destroy(0); }\n')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libpldepth_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.split()[0] == "100"

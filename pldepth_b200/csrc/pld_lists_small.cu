@@ -35,7 +35,7 @@ __device__ __forceinline__ void draw_philox(const ListParams& P, uint32_t off_lo
 }
 
 #ifndef PLD_SMALL_MINBLOCKS
-#define PLD_SMALL_MINBLOCKS 1
+#define PLD_SMALL_MINBLOCKS 2
 #endif
 template <int K, int SRC, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {

@@ -20,7 +20,7 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
   P.ticket = ctx->d_ticket;
   if (loss) {
     // upper bound of the grid either launcher picks
-    const int per_image_cap = (ctx->num_sms * 8 + P.B - 1) / P.B;
+    const int per_image_cap = lists_per_image_cap(ctx->num_sms, P.B);
     int rc = ctx->ensure_partials(per_image_cap * P.B + P.B);
     if (rc) return rc;
     P.partials = ctx->d_partials;

@@ -55,6 +55,11 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     }                                                                                      \
   } while (0)
 
+// CTAs per image of the list kernels: enough CTAs per SM that the hardware scheduler evens out the tail
+// (measured at config 2: 8 CTAs/SM 153 us, 4 -> 176 us, 2 -> 202 us; PLD_GRID_MULT overrides for experiments).
+int lists_grid_mult();
+inline int lists_per_image_cap(int num_sms, int B) { return (num_sms * lists_grid_mult() + B - 1) / B; }
+
 }  // namespace pld
 
 struct pld_ctx {

@@ -389,7 +389,7 @@ int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cud
   else if (K <= 128) lpl = 16;
   else lpl = 32;
   const int gpb = 256 / lpl;
-  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  const int per_image_cap = lists_per_image_cap(num_sms, P.B);
   int gx = (P.n + gpb - 1) / gpb;
   if (gx > per_image_cap) gx = per_image_cap;
   if (gx < 1) gx = 1;

@@ -315,7 +315,7 @@ static int launch_small_k(const ListParams& P, dim3 grid, cudaStream_t st) {
 }
 
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st) {
-  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  const int per_image_cap = lists_per_image_cap(num_sms, P.B);
   int gx = (P.n + 255) / 256;
   if (gx > per_image_cap) gx = per_image_cap;
   if (gx < 1) gx = 1;
@@ -338,7 +338,7 @@ int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st) 
 }
 
 int launch_lists_small(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st) {
-  const int per_image_cap = (num_sms * 8 + P.B - 1) / P.B;
+  const int per_image_cap = lists_per_image_cap(num_sms, P.B);
   int gx = (P.n + 255) / 256;
   if (gx > per_image_cap) gx = per_image_cap;
   if (gx < 1) gx = 1;

@@ -1,6 +1,7 @@
 // Context, error plumbing and the auxiliary kernels of the sampler: valid-pixel table,
 // MT19937 stream + NumPy masked rejection, gt min/max, candidate scores, top-R selection.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pld_common.cuh"
@@ -18,6 +19,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return t_err; }
+
+int lists_grid_mult() {
+  static int m = 0;
+  if (m == 0) {
+    const char* e = getenv("PLD_GRID_MULT");
+    m = e ? atoi(e) : 8;
+    if (m < 1 || m > 1024) m = 8;
+  }
+  return m;
+}
 
 }  // namespace pld
 

@@ -397,7 +397,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   int* counts = (int*)((char*)ctx->d_scratch + off_counts);
   int32_t* nv = n_valid ? n_valid : (int32_t*)((char*)ctx->d_scratch + off_nv);
   float2* table = (float2*)((char*)ctx->d_scratch + off_tab);
-  const int per_image_cap = (ctx->num_sms * 8 + B - 1) / B;
+  const int per_image_cap = lists_per_image_cap(ctx->num_sms, B);
   rc = ctx->ensure_partials(per_image_cap * B + B);
   if (rc) return rc;
 
@@ -512,7 +512,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   unsigned long long* varying = bits_or + 2 * B;
   uint32_t* order = (uint32_t*)(sb + o_order);
   float2* table = (float2*)(sb + o_tab);
-  const int per_image_cap = (ctx->num_sms * 8 + B - 1) / B;
+  const int per_image_cap = lists_per_image_cap(ctx->num_sms, B);
   rc = ctx->ensure_partials(per_image_cap * B + B);
   if (rc) return rc;
 

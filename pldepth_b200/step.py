@@ -36,8 +36,8 @@ class FusedPLStep(object):
         default_f = {"purely": 1.0, "masked": 1.5, "thresholded": 1.5, "information": 5}[strategy]
         self.n_candidates = int(self.R * (default_f if candidate_factor is None else candidate_factor))
         self.threshold, self.equality_penalty, self.promotion = threshold, equality_penalty, promotion
-        if strategy != "purely" and (self.K > 16 or self.n_candidates < self.R):
-            raise ValueError("scored strategies need ranking_size <= 16 and candidate_factor >= 1 on the fused path")
+        if strategy != "purely" and self.n_candidates < self.R:
+            raise ValueError("scored strategies need candidate_factor >= 1")
 
     def _buffers(self, B, H, W, Hm, Wm, dev):
         key = (B, H, W, Hm, Wm, dev)
@@ -74,6 +74,23 @@ class FusedPLStep(object):
         gb = self.global_batch if self.global_batch else B
         scale = 1.0 / (float(gb) * float(self.R))
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+        if self.strategy != "purely" and self.K > 16:
+            # long lists: the scoring pass of the fused kernel is register-resident (K <= 16); above that the
+            # staged calls do the same work (candidates are materialised once)
+            vf, nv = ops.mask_compact(mask, H, W)
+            cand, _ = ops.sample_lists_philox(gt, vf, nv, self.K, self.n_candidates, self.seed, self.step_index,
+                                              self.image_base)
+            mm = ops.gt_minmax(gt) if self.strategy == "information" else None
+            scores = ops.score_lists(cand, self.strategy, self.threshold, self.equality_penalty, self.promotion, mm)
+            top, _ = ops.select_top(scores, cand, self.R)
+            loss, loss_sum, grad, _ = ops.listmle_fwd_bwd(top, pred, B, self.K, scale, grad_out=buf["grad"])
+            buf["loss"].copy_(loss)
+            buf["loss_sum"].copy_(loss_sum)
+            buf["n_valid"].copy_(nv)
+            if buf["rankings"] is not None:
+                buf["rankings"].copy_(top)
+            self.step_index += 1
+            return buf
         if self.strategy != "purely":
             from ._lib import STRATEGY, PROMOTION
             check(lib.pld_fused_step_scored(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K,

@@ -289,8 +289,14 @@ def test_fused_step_object_with_strategy(cuda_device):
     out = st.run(gt_d, mask_d, pred_d)
     ref = ops.fused_step_scored(mask_d, gt_d, pred_d, K, int(R * 1.5), R, "thresholded", seed=3, offset=0)
     assert torch.equal(out["rankings"], ref["rankings"]) and out["loss"].item() == ref["loss"].item()
+    # long lists fall back to the staged calls inside the same object
+    st20 = FusedPLStep(20, 50, seed=3, strategy="masked")
+    out20 = st20.run(gt_d, mask_d, pred_d)
+    want_loss, want_grad, _ = lo.hourglass_nll(out20["rankings"].cpu().numpy(), pred, B, 20)
+    assert_close(out20["loss"].item(), want_loss, "K=20 scored loss")
+    assert_close(out20["grad"].cpu().numpy(), want_grad, "K=20 scored gradient")
     with pytest.raises(ValueError):
-        FusedPLStep(20, R, strategy="masked")
+        FusedPLStep(5, R, strategy="masked", candidate_factor=0.5)
 
 
 @pytest.mark.parametrize("B,H,W,K,n", [(1, 7, 9, 3, 1), (2, 5, 5, 1, 40), (1, 31, 33, 5, 255), (3, 17, 19, 16, 257),

@@ -198,6 +198,8 @@ int pld_gather_predictions(pld_ctx* ctx, const float* rankings, const float* pre
  * its gradient (nll_loss.py:32-62).  Three launches: mask analysis (+ zeroing of grad), per-image
  * 8-byte lookup tables in context scratch, fused list kernel.  Outputs are identical to
  * pld_mask_compact + pld_fused_sample_loss_bwd with the same (seed, offset, image_base).
+ * With rankings == NULL holed masks take the valid-index mode (one table gather per draw instead of two; the
+ * gradient is accumulated per valid pixel and expanded once), results unchanged.
  *   mask f32[B,Hm,Wm], gt f32[B,H*W], pred f32[B,H*W]
  *   -> n_valid i32[B] (nullable; negative = identity table, see pld_mask_compact),
  *      rankings f32[B,n,K,2] (nullable), loss f32[1], loss_sum f64[1] (nullable),

@@ -26,6 +26,9 @@ struct ListParams {
   float* per_list;             // [B*n] nullable
   float* grad;                 // [B, HW] nullable
   long long* acc;              // [B, HW] fixed-point (2^-32) accumulators: deterministic mode, else null
+  // valid-index mode (holed masks, rankings not emitted): tables hold (gt, pred) by valid index for EVERY image and
+  // the gradient of a holed image accumulates by valid index here [B, table_stride]; expanded to pixels afterwards
+  float* grad_valid;
   float* loss;                 // [1]
   double* loss_sum;            // [1] nullable
   double* partials;
@@ -62,12 +65,12 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 
 // gradient contribution of one point: float RED (fast) or 64-bit fixed-point atomic (integer addition is
 // associative, so the dense gradient is bit-reproducible); `g` is the unscaled d nll / d score
-__device__ __forceinline__ void grad_add(const ListParams& P, size_t idx, float g) {
+__device__ __forceinline__ void grad_add(const ListParams& P, float* dst_base, size_t acc_base, int idx, float g) {
   if (P.acc != nullptr) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(P.acc) + idx,
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.acc) + acc_base + (size_t)idx,
               (unsigned long long)__double2ll_rn((double)g * 4294967296.0));
   } else {
-    red_add_f32(P.grad + idx, g * P.scale);
+    red_add_f32(dst_base + idx, g * P.scale);
   }
 }
 

@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
   }
 
+  const bool vj = (SRC == SRC_PHILOX_TAB) && !identity && P.grad_valid != nullptr;
+  const bool gs_layout = identity || vj;
+  float* grad_dst = P.grad == nullptr ? nullptr
+                    : (vj ? P.grad_valid + (size_t)b * P.table_stride : P.grad + map_off);
+
   if (M != 0) {
     for (int l0 = blockIdx.x * GPB + (threadIdx.x >> 5) * GPW; l0 < P.n; l0 += gridDim.x * GPB) {
       const int lraw = l0 + lane / LPL;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
           float2 t[IPL];
 #pragma unroll
           for (int i = 0; i < IPL; ++i) t[i] = __ldg(tab + sel[i]);
-          if (identity) {  // entry j = (gt[j], pred[j]); the prediction rides through the sort as payload
+          if (gs_layout) {  // entry j = (gt, pred) of the j-th valid pixel; the prediction is parked per draw slot
 #pragma unroll
             for (int i = 0; i < IPL; ++i) {
               const bool on = (emask >> i) & 1u;
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
           if (P.grad != nullptr) {
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
-              if (((emask & ~inval) >> i) & 1u) grad_add(P, map_off + (size_t)p[i], ex[i] * (cl[i] + cpre) - 1.0f);
+              if (((emask & ~inval) >> i) & 1u) grad_add(P, grad_dst, map_off, p[i], ex[i] * (cl[i] + cpre) - 1.0f);
           }
         }
       }

@@ -64,6 +64,12 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     vflat = P.valid_flat + (size_t)b * (size_t)P.valid_stride;
   }
 
+  // table layout / gradient destination of this image (see ListParams::grad_valid)
+  const bool vj = (SRC == SRC_PHILOX_TAB) && !identity && P.grad_valid != nullptr;
+  const bool gs_layout = identity || vj;
+  float* grad_dst = P.grad == nullptr ? nullptr
+                    : (vj ? P.grad_valid + (size_t)b * P.table_stride : P.grad + map_off);
+
   // Philox list id of the l-th list of this image: l itself, or the l-th best candidate of a
   // previous scoring pass
   const uint32_t* __restrict__ lmap = nullptr;
@@ -189,8 +195,9 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
         }
         if (SRC == SRC_PHILOX_TAB) {
           // per-image lookup table built by prep_build_kernel: one 8-byte gather per draw
-          if (identity) {
-            // full mask: entry j = (gt[j], pred[j]); the prediction rides through the sort as payload
+          if (gs_layout) {
+            // entry j = (gt, pred) of the j-th valid pixel (full mask: of pixel j); the prediction rides through
+            // the sort as payload
             uint32_t spay[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           if (P.grad != nullptr) {
 #pragma unroll
             for (int k = 0; k < K; ++k)
-              if (!((inval >> k) & 1u)) grad_add(P, map_off + (size_t)p[k], g[k]);
+              if (!((inval >> k) & 1u)) grad_add(P, grad_dst, map_off, p[k], g[k]);
           }
         }
       }

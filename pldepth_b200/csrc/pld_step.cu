@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const float* __r
 __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     const float* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
     int W, int HW, double xs, double ys, int identity_scale, int nchunks, const int* __restrict__ counts,
-    float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid) {
+    float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid, int32_t* __restrict__ vj_flat,
+    float* __restrict__ grad_valid) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
   int pre = 0, all = 0;
@@ -124,6 +125,14 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
     return;
   }
+  if (grad_valid != nullptr) {   // holed image in valid-index mode: clear its accumulators (valid count <= Nm)
+    float* gv = grad_valid + (size_t)b * table_stride;
+#pragma unroll 4
+    for (int i = 0; i < PC_ITEMS; ++i) {
+      const int j = chunk * PC_CHUNK + i * PC_THREADS + threadIdx.x;
+      if (j < Nm) gv[j] = 0.f;
+    }
+  }
   // Compaction with lane-consecutive pixels: warp w of the CTA owns pixels
   // [chunk*CHUNK + w*512, +512) as 16 rows of 32; ballots give each valid pixel its rank, so mask
   // reads, gt reads and table writes are all coalesced.
@@ -156,7 +165,13 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
         const int rm = idx / Wm, cm = idx - rm * Wm;
         p = (int)((double)rm * xs) * W + (int)((double)cm * ys);  // sampling.py:115-119
       }
-      tab[rank + __popc(bal[i] & lt)] = make_float2(__int_as_float(p), __ldg(g + p));
+      const int pos = rank + __popc(bal[i] & lt);
+      if (vj_flat != nullptr) {   // valid-index mode: (gt, pred) by valid index + the pixel of every valid index
+        tab[pos] = make_float2(__ldg(g + p), __ldg(pred + (size_t)b * HW + p));
+        vj_flat[(size_t)b * table_stride + pos] = p;
+      } else {
+        tab[pos] = make_float2(__int_as_float(p), __ldg(g + p));
+      }
     }
     rank += __popc(bal[i]);
   }
@@ -370,6 +385,21 @@ __global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restri
   }
 }
 
+// valid-index mode: scatter the per-valid-index gradient of every holed image to its pixels (the dense map was
+// zeroed by prep_count_kernel; full-mask images accumulated straight into it)
+__global__ void __launch_bounds__(256) vj_expand_kernel(const float* __restrict__ grad_valid,
+                                                        const int32_t* __restrict__ vj_flat,
+                                                        const int32_t* __restrict__ n_valid, size_t table_stride, int HW,
+                                                        float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  const int M = n_valid[b];
+  if (M <= 0) return;   // identity table (negative count) or empty mask
+  const float* gv = grad_valid + (size_t)b * table_stride;
+  const int32_t* vf = vj_flat + (size_t)b * table_stride;
+  float* gr = grad + (size_t)b * HW;
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < M; j += gridDim.x * 256) gr[vf[j]] = gv[j];
+}
+
 }  // namespace pld
 
 using namespace pld;
@@ -392,11 +422,18 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t off_counts = 0, off_nv = al(sizeof(int) * (size_t)B * nchunks);
   const size_t off_tab = off_nv + al(sizeof(int32_t) * (size_t)B);
-  int rc = ctx->ensure_scratch(off_tab + sizeof(float2) * (size_t)B * tstride);
+  // valid-index mode: holed masks, gradient wanted, rankings not materialised (nothing needs the pixel index)
+  const bool vj_mode = (rankings == nullptr) && (grad != nullptr) && !ctx->deterministic;
+  const size_t off_vjf = off_tab + al(sizeof(float2) * (size_t)B * tstride);
+  const size_t off_gv = off_vjf + (vj_mode ? al(sizeof(int32_t) * (size_t)B * tstride) : 0);
+  const size_t scratch_total = off_gv + (vj_mode ? al(sizeof(float) * (size_t)B * tstride) : 0);
+  int rc = ctx->ensure_scratch(scratch_total);
   if (rc) return rc;
   int* counts = (int*)((char*)ctx->d_scratch + off_counts);
   int32_t* nv = n_valid ? n_valid : (int32_t*)((char*)ctx->d_scratch + off_nv);
   float2* table = (float2*)((char*)ctx->d_scratch + off_tab);
+  int32_t* vj_flat = vj_mode ? (int32_t*)((char*)ctx->d_scratch + off_vjf) : nullptr;
+  float* grad_valid = vj_mode ? (float*)((char*)ctx->d_scratch + off_gv) : nullptr;
   const int per_image_cap = lists_per_image_cap(ctx->num_sms, B);
   rc = ctx->ensure_partials(per_image_cap * B + B);
   if (rc) return rc;
@@ -417,7 +454,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
   prep_build_kernel<<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv);
+                                                table, tstride, nv, vj_flat, grad_valid);
   PLD_CHECK_LAUNCH();
   if (n == 0) {
     PLD_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
@@ -432,6 +469,7 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
+  P.grad_valid = grad_valid;
   if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
   if (grad != nullptr && ctx->deterministic) {
     rc = ctx->ensure_acc(gtotal);
@@ -443,6 +481,12 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   rc = (K <= 16) ? launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st)
                  : launch_lists_large(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
+  if (rc == PLD_OK && vj_mode) {
+    int gx = (int)((tstride + 255) / 256);
+    if (gx > per_image_cap) gx = per_image_cap;
+    vj_expand_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(grad_valid, vj_flat, nv, tstride, HW, grad);
+    PLD_CHECK_LAUNCH();
+  }
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   if (rc == PLD_OK && ctx->use_device_offset) rc = launch_offset_advance(ctx, st);
   return rc;
@@ -533,7 +577,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
   prep_build_kernel<<<pgrid, PC_THREADS, 0, st>>>(mask, gt, pred ? pred : gt, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks,
-                                                 counts, table, tstride, nv);
+                                                 counts, table, tstride, nv, nullptr, nullptr);
   PLD_CHECK_LAUNCH();
   if (strategy == PLD_STRATEGY_INFORMATION) {
     gt_minmax_step_kernel<<<B, 256, 0, st>>>(gt, HW, minmax);

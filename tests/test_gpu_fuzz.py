@@ -58,6 +58,12 @@ def test_random_core_step(cuda_device, seed):
         err = np.abs(grad.cpu().numpy() - want_grad).max() / np.abs(want_grad).max()
         assert err <= 1e-5
         assert np.abs(pl.cpu().numpy() - want_pl).max() <= 1e-5 * np.abs(want_pl).max()
+    # no materialised rankings (valid-index accumulation on holed masks)
+    loss4, _, grad4, _, _, _ = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=s, offset=off, image_base=base,
+                                              want_rankings=False)
+    assert loss4.item() == loss.item()
+    if K > 1:
+        assert np.abs(grad4.cpu().numpy() - want_grad).max() / np.abs(want_grad).max() <= 1e-5
     # the fed-ranking loss (Keras signature path) on the same lists
     loss3, _, grad3, _ = ops.listmle_fwd_bwd(rank, pred_d, B, K, 1.0 / (B * n))
     assert abs(loss3.item() - want_loss) <= 1e-5 * max(abs(want_loss), 1e-12)

@@ -176,6 +176,11 @@ def test_one_call_step_equals_staged_calls(cuda_device, K, n, geometry):
     for b in range(B):                          # never a masked-out pixel
         valid = set(so.valid_flat_indices(mask[b], (H, W)).tolist())
         assert set(rank[b, :, :, 0].long().flatten().tolist()) <= valid
+    # without materialising the rankings (valid-index gradient accumulation for holed masks): same loss, same gradient
+    loss3, ls3, grad3, rank3, pl3, nv3 = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=5, offset=9, image_base=2,
+                                                        want_rankings=False, want_per_list=True)
+    assert rank3 is None and torch.equal(pl3, pl) and loss3.item() == loss.item() and torch.equal(nv3, nv)
+    assert_close(grad3.cpu().numpy(), want_grad, "gradient without emitted rankings")
 
 
 def test_loss_is_deterministic(cuda_device):

@@ -216,6 +216,8 @@ int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float
  * REDRAWN from their Philox list ids inside the fused kernel that emits rankings / loss / gradient.
  * Results equal pld_sample_lists_philox(n) -> pld_score_lists -> pld_select_top(R) -> pld_listmle_fwd_bwd.
  * pred / loss / grad may be NULL (sampler only: rankings and order_out).  ranking_size 1..16.
+ * With rankings == NULL nobody observes the order of the kept lists (the loss is invariant to it): the sort is
+ * replaced by an exact radix selection and order_out lists the kept candidates in ascending candidate order.
  *   -> order_out i32[B,R] (nullable): candidate index of every kept list */
 int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
                           int Wm, int H, int W, int K, int n, int R, int strategy, double threshold,

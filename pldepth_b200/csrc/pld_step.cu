@@ -211,11 +211,12 @@ __global__ void __launch_bounds__(256) gt_minmax_step_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B,
-                                                       unsigned long long* bits_or, unsigned long long* bits_and) {
+                                                       unsigned long long* bits_or, unsigned long long* bits_and,
+                                                       uint64_t* iprefix) {
   for (int i = blockIdx.x * 256 + threadIdx.x; i < B * SEL_BINS; i += gridDim.x * 256) hist[i] = 0u;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < B; i += 256) {
-      prefix[i] = 0ull; remaining[i] = R; bits_or[i] = 0ull; bits_and[i] = ~0ull;
+      prefix[i] = 0ull; remaining[i] = R; bits_or[i] = 0ull; bits_and[i] = ~0ull; iprefix[i] = 0ull;
     }
 }
 
@@ -366,6 +367,153 @@ __global__ void sel_varying_kernel(const unsigned long long* bits_or, const unsi
   if (b < B) varying[b] = bits_or[b] ^ bits_and[b];
 }
 
+// ------------------------------------------------------------------------------------------
+// Unordered top-R (rankings not materialised: the loss does not depend on the order of the lists).  Instead of
+// sorting the survivors, the radix selection is refined on them down to the exact (key, candidate index) cut:
+// three more passes over the remaining 28 key bits, two over the 23 index bits (ties: larger index first),
+// each restricted to the boundary bucket of the previous pass.  Kept candidates are then compacted in
+// candidate order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sel2_hist_kernel(const uint64_t* __restrict__ keys_s, const uint32_t* __restrict__ vals_s,
+                                                        const int* __restrict__ n_surv, size_t stride, int idx_pass,
+                                                        int shift, int nbits, const uint64_t* __restrict__ prefix,
+                                                        const uint64_t* __restrict__ iprefix, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_h[SEL_BINS];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < SEL_BINS; i += 256) s_h[i] = 0u;
+  __syncthreads();
+  const int n = n_surv[b];
+  const uint64_t* k = keys_s + (size_t)b * stride;
+  const uint32_t* v = vals_s + (size_t)b * stride;
+  const uint64_t pre = prefix[b], ipre = iprefix[b];
+  const uint32_t msk = (1u << nbits) - 1u;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const uint64_t key = k[i];
+    if (!idx_pass) {
+      if ((key >> (shift + nbits)) == pre) atomicAdd(&s_h[(uint32_t)(key >> shift) & msk], 1u);
+    } else if (key == pre) {
+      const uint32_t id = v[i];
+      if ((uint64_t)(id >> (shift + nbits)) == ipre) atomicAdd(&s_h[(id >> shift) & msk], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned int* h = hist + (size_t)b * SEL_BINS;
+  for (int i = threadIdx.x; i < SEL_BINS; i += 256)
+    if (s_h[i]) atomicAdd(h + i, s_h[i]);
+}
+
+// as sel_find_kernel, for a pass of `nbits` bits extending either the key prefix or the index prefix
+__global__ void __launch_bounds__(256) sel2_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
+                                                        uint64_t* __restrict__ iprefix, int* __restrict__ remaining,
+                                                        int idx_pass, int nbits) {
+  __shared__ unsigned int s_sum[256];
+  const int b = blockIdx.x;
+  unsigned int* h = hist + (size_t)b * SEL_BINS;
+  const int hi = SEL_BINS - 16 * threadIdx.x;
+  unsigned int loc[16], tot = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { loc[i] = h[hi - 1 - i]; tot += loc[i]; }
+  s_sum[threadIdx.x] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int need = (unsigned int)remaining[b];
+    unsigned int above = 0;
+    int t = 0;
+    while (t < 255 && above + s_sum[t] < need) { above += s_sum[t]; ++t; }
+    s_sum[0] = (unsigned int)t;
+    s_sum[1] = above;
+  }
+  __syncthreads();
+  const int owner = (int)s_sum[0];
+  const unsigned int above0 = s_sum[1];
+  __syncthreads();
+  if ((int)threadIdx.x == owner) {
+    const unsigned int need = (unsigned int)remaining[b];
+    unsigned int above = above0;
+    int i = 0;
+    while (i < 15 && above + loc[i] < need) { above += loc[i]; ++i; }
+    const uint64_t bin = (uint64_t)(hi - 1 - i);
+    if (idx_pass) iprefix[b] = (iprefix[b] << nbits) | bin;
+    else prefix[b] = (prefix[b] << nbits) | bin;
+    remaining[b] = (int)(need - above);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[hi - 1 - i] = 0u;
+}
+
+__device__ __forceinline__ bool sel2_keep(uint64_t key, uint32_t id, uint64_t tkey, uint32_t tidx) {
+  return key > tkey || (key == tkey && id >= tidx);
+}
+
+__global__ void __launch_bounds__(SC_THREADS) sel2_count_kernel(const uint64_t* __restrict__ keys_s,
+                                                               const uint32_t* __restrict__ vals_s,
+                                                               const int* __restrict__ n_surv, size_t stride, int ntiles,
+                                                               const uint64_t* __restrict__ prefix,
+                                                               const uint64_t* __restrict__ iprefix, int* __restrict__ counts) {
+  __shared__ int s_warp[SC_THREADS / 32];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int n = n_surv[b];
+  const uint64_t* k = keys_s + (size_t)b * stride;
+  const uint32_t* v = vals_s + (size_t)b * stride;
+  const uint64_t tkey = prefix[b];
+  const uint32_t tidx = (uint32_t)iprefix[b];
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    const int idx = tile * SC_TILE + i * SC_THREADS + threadIdx.x;
+    if (idx < n && sel2_keep(k[idx], v[idx], tkey, tidx)) ++c;
+  }
+  const int tot = block_sum_int(c, s_warp);
+  if (threadIdx.x == 0) counts[b * ntiles + tile] = tot;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) sel2_compact_kernel(const uint64_t* __restrict__ keys_s,
+                                                                 const uint32_t* __restrict__ vals_s,
+                                                                 const int* __restrict__ n_surv, size_t stride, int ntiles,
+                                                                 const uint64_t* __restrict__ prefix,
+                                                                 const uint64_t* __restrict__ iprefix,
+                                                                 const int* __restrict__ counts, int R,
+                                                                 uint32_t* __restrict__ order, int32_t* __restrict__ order_out) {
+  __shared__ int s_warp[SC_THREADS / 32];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  int pre = 0;
+  for (int i = threadIdx.x; i < tile; i += SC_THREADS) pre += counts[b * ntiles + i];
+  const int prefix_cnt = block_sum_int(pre, s_warp);
+  const int n = n_surv[b];
+  const uint64_t* k = keys_s + (size_t)b * stride;
+  const uint32_t* v = vals_s + (size_t)b * stride;
+  const uint64_t tkey = prefix[b];
+  const uint32_t tidx = (uint32_t)iprefix[b];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wbase = tile * SC_TILE + wid * (SC_ITEMS * 32);
+  uint32_t bal[SC_ITEMS], id[SC_ITEMS];
+  int wcount = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    id[i] = (idx < n) ? v[idx] : 0u;
+    bal[i] = __ballot_sync(0xffffffffu, idx < n && sel2_keep(k[idx], id[i], tkey, tidx));
+    wcount += __popc(bal[i]);
+  }
+  __syncthreads();
+  if (lane == 0) s_warp[wid] = wcount;
+  __syncthreads();
+  int rank = prefix_cnt;
+  for (int i = 0; i < wid; ++i) rank += s_warp[i];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; ++i) {
+    if ((bal[i] >> lane) & 1u) {
+      const int pos = rank + __popc(bal[i] & lt);
+      if (pos < R) {   // exactly R are kept by construction; the guard only protects the buffer
+        order[(size_t)b * R + pos] = id[i];
+        if (order_out != nullptr) order_out[(size_t)b * R + pos] = (int32_t)id[i];
+      }
+    }
+    rank += __popc(bal[i]);
+  }
+}
+
 // kept candidates in final order (score descending): tail of the sorted survivors read backwards, taken from
 // whichever ping-pong buffer the image's last executed pass wrote
 __global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b,
@@ -508,6 +656,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   PLD_REQUIRE(strategy >= PLD_STRATEGY_MASKED && strategy <= PLD_STRATEGY_INFORMATION, "bad strategy");
   PLD_REQUIRE(promotion == PLD_PROMOTION_NEP50 || promotion == PLD_PROMOTION_LEGACY, "bad promotion");
   PLD_REQUIRE((offset >> 48) == 0, "offset must fit in 48 bits");
+  PLD_REQUIRE(n <= (1 << 23), "at most 2^23 candidate lists per image");
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W, Nm = Hm * Wm;
   const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
@@ -531,7 +680,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const size_t o_v0 = take(sizeof(uint32_t) * total);
   const size_t o_v1 = take(sizeof(uint32_t) * total);
   const size_t o_rhist = take(seg_radix_sort_hist_bytes(n, B));
-  const size_t o_bits = take(sizeof(unsigned long long) * 3 * (size_t)B);
+  const size_t o_bits = take(sizeof(unsigned long long) * 4 * (size_t)B);
   const size_t o_order = take(sizeof(uint32_t) * (size_t)B * R);
   const size_t o_tab = take(sizeof(float2) * (size_t)B * tstride);
   int rc = ctx->ensure_scratch(off);
@@ -554,6 +703,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   unsigned long long* bits_or = (unsigned long long*)(sb + o_bits);
   unsigned long long* bits_and = bits_or + B;
   unsigned long long* varying = bits_or + 2 * B;
+  uint64_t* iprefix = (uint64_t*)(bits_or + 3 * B);
   uint32_t* order = (uint32_t*)(sb + o_order);
   float2* table = (float2*)(sb + o_tab);
   const int per_image_cap = lists_per_image_cap(ctx->num_sms, B);
@@ -601,7 +751,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   // 3. radix top-R selection -> survivors in candidate order
   int gsel = (n + 255) / 256;
   if (gsel > per_image_cap) gsel = per_image_cap;
-  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and);
+  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and, iprefix);
   PLD_CHECK_LAUNCH();
   for (int pass = 0; pass < 3; ++pass) {
     sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
@@ -617,10 +767,25 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   sel_varying_kernel<<<(B + 255) / 256, 256, 0, st>>>(bits_or, bits_and, varying, B);
   PLD_CHECK_LAUNCH();
 
-  // 4. full order of the survivors (ascending, stable); the best R are the tail read backwards
-  rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, varying, st);
-  if (rc) return rc;
-  {
+  if (rankings == nullptr) {
+    // 4a. nobody sees the order of the kept lists: refine the selection to the exact cut instead of sorting
+    static const int kPass[5][3] = {{0, 16, 12}, {0, 4, 12}, {0, 0, 4}, {1, 11, 12}, {1, 0, 11}};  // idx?, shift, bits
+    for (int p = 0; p < 5; ++p) {
+      sel2_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(k0, v0, n_surv, (size_t)n, kPass[p][0], kPass[p][1],
+                                                                         kPass[p][2], prefix, iprefix, shist);
+      PLD_CHECK_LAUNCH();
+      sel2_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2]);
+      PLD_CHECK_LAUNCH();
+    }
+    sel2_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt);
+    PLD_CHECK_LAUNCH();
+    sel2_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt, R, order,
+                                                     order_out);
+    PLD_CHECK_LAUNCH();
+  } else {
+    // 4b. full order of the survivors (ascending, stable); the best R are the tail read backwards
+    rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, varying, st);
+    if (rc) return rc;
     int go = (R + 255) / 256;
     if (go > per_image_cap) go = per_image_cap;
     sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, v1, varying, n_surv, n, R, order, order_out);

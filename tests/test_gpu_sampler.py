@@ -289,6 +289,13 @@ def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K,
     out2 = ops.fused_step_scored(mask_d, gt_d, None, K, n, R, strategy, 0.03, -1000, promotion, seed=4, offset=2,
                                  image_base=1)
     assert torch.equal(out2["rankings"], top) and out2["loss"] is None
+    # rankings not materialised: exact radix selection instead of the sort -- same kept SET, same loss / gradient
+    out3 = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, promotion, seed=4, offset=2,
+                                 image_base=1, want_rankings=False, want_order=True)
+    assert out3["rankings"] is None
+    assert torch.equal(out3["order"], torch.sort(order, dim=1).values)
+    assert abs(out3["loss"].item() - want_loss) <= 1e-5 * abs(want_loss)
+    assert np.abs(out3["grad"].cpu().numpy() - want_grad).max() / np.abs(want_grad).max() <= 1e-5
 
 
 def test_strategy_classes_use_fast_path_consistently(cuda_device):

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--R", type=int, default=100000)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--no-emit", action="store_true", help="do not materialise the rankings (fused training step)")
     ap.add_argument("--graph", action="store_true", help="replay each fused step from a CUDA graph (FusedPLStep.capture)")
     args = ap.parse_args()
     from pldepth_b200 import ops, sampling, synth
@@ -45,11 +46,11 @@ def main():
                 return ops.listmle_fwd_bwd(y, pred, B, K, 1.0 / (B * y.shape[1]))
             n = int(R * s._default_factor)          # one call: score pass, top-R, redraw + loss + gradient
             return ops.fused_step_scored(mask, gt, pred, K, n, R, s._strategy, 0.03, -1000, "nep50", seed=1,
-                                         offset=step.i)
+                                         offset=step.i, want_rankings=not args.no_emit)
         step.i = 0
         if args.graph and not name.startswith("purely"):
             from pldepth_b200.step import FusedPLStep
-            fs = FusedPLStep(K, R, seed=1, strategy=s._strategy)
+            fs = FusedPLStep(K, R, seed=1, strategy=s._strategy, emit_rankings=not args.no_emit)
             graph, _ = fs.capture(gt, mask, pred)
             step = graph.replay
         for _ in range(3):
@@ -66,7 +67,8 @@ def main():
         launches = (Context.current(0).lib.pld_launch_count() - l0) / args.steps
         if args.graph:
             Context.current(0).device_offset(False)
-        print(json.dumps({"strategy": name, "cuda_graph": bool(args.graph and not name.startswith("purely")), "candidate_factor": s._default_factor if f is None else f,
+        print(json.dumps({"strategy": name, "cuda_graph": bool(args.graph and not name.startswith("purely")),
+                          "rankings": "not materialised" if args.no_emit else "emitted", "candidate_factor": s._default_factor if f is None else f,
                           "kept_lists_per_s": B * R / (ms * 1e-3), "ms_per_step": ms, "launches_per_step": launches,
                           "shape": "B=%d %dx%d K=%d R=%d" % (B, H, W, K, R)}))
 

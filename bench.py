@@ -208,6 +208,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # pinned host buffers of the e2e leg should live on the GPU's own NUMA node (first touch)
+    from pldepth_b200.hostbind import bind_to_gpu_numa
+    numa = ({"bound": False, "why": "PLD_NUMA_BIND=0"} if os.environ.get("PLD_NUMA_BIND", "1") == "0"
+            else bind_to_gpu_numa(local_rank))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -376,7 +380,7 @@ def run_b200(args):
            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
            "api": "HostPipelinedStep.submit/result: pinned host gt+mask+pred -> device, fused step, loss + dense "
                   "gradient -> pinned host; 2 slots, H2D / compute / D2H streams overlap across steps",
-           "last_loss": loss_host}
+           "last_loss": loss_host, "host_numa": numa}
 
     if rank == 0:
         line = {

@@ -487,12 +487,13 @@ __global__ void __launch_bounds__(256) select_keys_kernel(const double* __restri
 __global__ void __launch_bounds__(256) select_gather_kernel(const uint32_t* __restrict__ vals,
                                                             const float* __restrict__ rankings, int n,
                                                             int K, int R, float* __restrict__ out,
-                                                            int32_t* __restrict__ order_out) {
-  // one warp per kept list: copies K float2
+                                                            int32_t* __restrict__ order_out, int direct) {
+  // one warp per kept list: copies K float2.  vals: sorted candidate ids of the image, best LAST (stride n), or
+  // (direct) the kept ids in output order (stride R)
   const int b = blockIdx.y;
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < R; j += gridDim.x * warps) {
-    const uint32_t src = vals[(size_t)b * n + (size_t)(n - 1 - j)];  // candidate index inside image b
+    const uint32_t src = direct ? vals[(size_t)b * R + j] : vals[(size_t)b * n + (size_t)(n - 1 - j)];
     const float2* s = reinterpret_cast<const float2*>(rankings) + ((size_t)b * n + src) * K;
     float2* d = reinterpret_cast<float2*>(out) + ((size_t)b * R + j) * K;
     for (int k = lane; k < K; k += 32) d[k] = __ldg(s + k);
@@ -504,6 +505,10 @@ int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
                    const unsigned long long* varying, cudaStream_t st);
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
+bool select_small_fits(int n);
+int select_small_init();
+int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
+                 uint32_t* order, int32_t* order_out, cudaStream_t st);
 
 }  // namespace pld
 
@@ -528,6 +533,8 @@ static int ctx_init(pld_ctx* c, int device) {
   PLD_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
   PLD_CUDA(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
   int rc = c->ensure_partials(4096);
+  if (rc) return rc;
+  rc = select_small_init();
   if (rc) return rc;
   PLD_CUDA(cudaDeviceSynchronize());
   return PLD_OK;
@@ -725,15 +732,24 @@ int pld_select_top(pld_ctx* ctx, const double* scores, const float* rankings, in
   uint32_t* v1 = (uint32_t*)base; base += al(total * 4);
   int* hist = (int*)base;
   const int cap = (ctx->num_sms * 8 + B - 1) / B;
+  int gxr = (R + 7) / 8;
+  if (gxr > cap) gxr = cap;
+  if (select_small_fits(n)) {
+    // the sizes the reference runs (R = 100 ... 1000 per image): one shared-memory sort per image
+    uint32_t* order = v0;
+    rc = select_small(nullptr, scores, n, (size_t)n, B, R, false, order, nullptr, st);
+    if (rc) return rc;
+    select_gather_kernel<<<dim3((unsigned)gxr, (unsigned)B), 256, 0, st>>>(order, rankings, n, K, R, rankings_out, order_out, 1);
+    PLD_CHECK_LAUNCH();
+    return PLD_OK;
+  }
   int gx = (n + 255) / 256;
   if (gx > cap) gx = cap;
   select_keys_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(scores, n, k0, v0);
   PLD_CHECK_LAUNCH();
   rc = seg_radix_sort(ctx, k0, v0, k1, v1, nullptr, n, (size_t)n, B, hist, nullptr, st);
   if (rc) return rc;
-  int gxr = (R + 7) / 8;
-  if (gxr > cap) gxr = cap;
-  select_gather_kernel<<<dim3((unsigned)gxr, (unsigned)B), 256, 0, st>>>(v0, rankings, n, K, R, rankings_out, order_out);
+  select_gather_kernel<<<dim3((unsigned)gxr, (unsigned)B), 256, 0, st>>>(v0, rankings, n, K, R, rankings_out, order_out, 0);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

@@ -8,6 +8,7 @@
 // The sort is ascending and stable; the consumer reads the tail of each segment backwards, which
 // yields "score descending, ties: larger candidate index first" (= reversed stable argsort).
 #include "pld_common.cuh"
+#include "pld_score.cuh"
 
 namespace pld {
 
@@ -173,6 +174,109 @@ int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(keys, vals, keys_tmp, vals_tmp, seg, pass, nblk, hist, dig_off);
     PLD_CHECK_LAUNCH();
   }
+  return PLD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small images of candidates (n <= SS_MAX per image, the sizes the reference itself runs: R = 100 ... 1000 lists per
+// image, sampling.py:157,190,218): one CTA per image loads every (key, candidate) pair into shared memory, orders
+// them with a bitonic network by (key descending, candidate index descending) -- exactly "reversed stable argsort"
+// -- and writes the best R.  One launch instead of selection + eight radix passes.
+// ------------------------------------------------------------------------------------------
+constexpr int SS_THREADS = 1024;
+constexpr int SS_MAX = 8192;
+
+template <bool FROM_SCORES>
+__global__ void __launch_bounds__(SS_THREADS) sel_small_kernel(const void* __restrict__ src, int n, size_t stride, int R,
+                                                              int N2, int ascending_ids, uint32_t* __restrict__ order,
+                                                              int32_t* __restrict__ order_out) {
+  extern __shared__ __align__(16) unsigned char ss_raw[];
+  uint64_t* s_key = reinterpret_cast<uint64_t*>(ss_raw);
+  uint32_t* s_id = reinterpret_cast<uint32_t*>(ss_raw + sizeof(uint64_t) * (size_t)N2);
+  __shared__ int s_cnt[256];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < N2; i += SS_THREADS) {
+    uint64_t k = 0ull;
+    if (i < n) {
+      if (FROM_SCORES) k = score_key(reinterpret_cast<const double*>(src)[(size_t)b * stride + i]);
+      else k = reinterpret_cast<const uint64_t*>(src)[(size_t)b * stride + i];
+    }
+    s_key[i] = k;
+    s_id[i] = (i < n) ? (uint32_t)i : 0u;   // pads: (0, 0) -- not larger than any real pair
+  }
+  __syncthreads();
+  for (int k = 2; k <= N2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (N2 >> 1); t += SS_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const uint64_t ka = s_key[i], kb = s_key[p];
+        const uint32_t ia = s_id[i], ib = s_id[p];
+        const bool a_lt_b = (ka < kb) || (ka == kb && ia < ib);
+        if (a_lt_b == ((i & k) == 0)) {   // descending where bit k of i is clear
+          s_key[i] = kb; s_key[p] = ka;
+          s_id[i] = ib; s_id[p] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!ascending_ids) {
+    for (int t = threadIdx.x; t < R; t += SS_THREADS) {
+      const uint32_t c = s_id[t];
+      if (order != nullptr) order[(size_t)b * R + t] = c;
+      if (order_out != nullptr) order_out[(size_t)b * R + t] = (int32_t)c;
+    }
+    return;
+  }
+  // kept candidates in ascending candidate order (the contract of the unordered selection): bitmap + scan
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_key);   // the keys are no longer needed
+  const int nwords = N2 >> 5;   // N2 >= 64; N2 / 32 words always fit in the N2 * 8 bytes of the key array
+  __syncthreads();
+  if ((int)threadIdx.x < nwords) s_bits[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int t = threadIdx.x; t < R; t += SS_THREADS) {
+    const uint32_t c = s_id[t];
+    atomicOr(&s_bits[c >> 5], 1u << (c & 31u));
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) s_cnt[threadIdx.x] = ((int)threadIdx.x < nwords) ? __popc(s_bits[threadIdx.x]) : 0;
+  __syncthreads();
+  if ((int)threadIdx.x < nwords) {
+    int pos = 0;
+    for (int w = 0; w < (int)threadIdx.x; ++w) pos += s_cnt[w];
+    uint32_t bits = s_bits[threadIdx.x];
+    while (bits) {
+      const uint32_t c = (threadIdx.x << 5) + (uint32_t)(__ffs((int)bits) - 1);
+      bits &= bits - 1u;
+      if (order != nullptr) order[(size_t)b * R + pos] = c;
+      if (order_out != nullptr) order_out[(size_t)b * R + pos] = (int32_t)c;
+      ++pos;
+    }
+  }
+}
+
+bool select_small_fits(int n) { return n >= 1 && n <= SS_MAX; }
+
+// raises the dynamic shared-memory limit of the kernels above on the current device (called by pld_ctx_create)
+int select_small_init() {
+  const int bytes = SS_MAX * (int)(sizeof(uint64_t) + sizeof(uint32_t));
+  PLD_CUDA(cudaFuncSetAttribute(sel_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PLD_CUDA(cudaFuncSetAttribute(sel_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return PLD_OK;
+}
+
+// best R of the n candidates of every image; exactly one of keys / scores is given
+int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
+                 uint32_t* order, int32_t* order_out, cudaStream_t st) {
+  int N2 = 64;
+  while (N2 < n) N2 <<= 1;
+  const size_t smem = (size_t)N2 * (sizeof(uint64_t) + sizeof(uint32_t));
+  if (scores != nullptr)
+    sel_small_kernel<true><<<B, SS_THREADS, smem, st>>>(scores, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out);
+  else
+    sel_small_kernel<false><<<B, SS_THREADS, smem, st>>>(keys, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out);
+  PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
 

@@ -23,6 +23,9 @@ int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
                    const unsigned long long* varying, cudaStream_t st);
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
+bool select_small_fits(int n);
+int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
+                 uint32_t* order, int32_t* order_out, cudaStream_t st);
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_ITEMS = 16;
@@ -748,6 +751,11 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   rc = launch_lists_small_score(P, ctx->num_sms, st);
   if (rc) return rc;
 
+  if (select_small_fits(n)) {
+    // 3'. few candidates per image (the sizes the reference runs): one shared-memory sort per image
+    rc = select_small(keys, nullptr, n, (size_t)n, B, R, rankings == nullptr, order, order_out, st);
+    if (rc) return rc;
+  } else {
   // 3. radix top-R selection -> survivors in candidate order
   int gsel = (n + 255) / 256;
   if (gsel > per_image_cap) gsel = per_image_cap;
@@ -790,6 +798,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     if (go > per_image_cap) go = per_image_cap;
     sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, v1, varying, n_surv, n, R, order, order_out);
     PLD_CHECK_LAUNCH();
+  }
   }
 
   // 5. redraw the kept lists from their Philox ids: emit rankings, loss and gradient

@@ -160,11 +160,15 @@ def test_sampler_classes_reproduce_reference_goldens(cuda_device, path, rng):
 
 @pytest.mark.parametrize("strategy", ["masked", "thresholded", "information"])
 @pytest.mark.parametrize("promotion", ["nep50", "legacy"])
-@pytest.mark.parametrize("K", [2, 5, 7, 8, 9, 20, 130, 300])
-def test_scores_and_selection_match_oracle(cuda_device, strategy, promotion, K):
+@pytest.mark.parametrize("K,n,R", [(2, 500, 333), (5, 500, 333), (7, 500, 333), (8, 500, 333), (9, 500, 333),
+                                   (20, 500, 333), (130, 500, 333), (300, 500, 333),
+                                   # more than 8192 candidates per image: segmented radix sort instead of the
+                                   # shared-memory sort
+                                   (5, 9000, 4100), (9, 8193, 8193), (20, 12000, 1)])
+def test_scores_and_selection_match_oracle(cuda_device, strategy, promotion, K, n, R):
     from pldepth_b200 import ops
     from tests.golden.make_golden import near_threshold_gt
-    H, W, B, n, R = 48, 40, 3, 500, 333
+    H, W, B = 48, 40, 3
     rs = np.random.RandomState(K)
     gt = np.stack([near_threshold_gt(H, W, 7 * K + b) for b in range(B)])
     mask = np.ones((B, H, W), np.float32)
@@ -250,14 +254,15 @@ def test_provider_mirror_per_image_and_batched(cuda_device):
 @pytest.mark.parametrize("strategy", ["masked", "thresholded", "information"])
 @pytest.mark.parametrize("promotion", ["nep50", "legacy"])
 @pytest.mark.parametrize("K,geometry", [(2, "full"), (5, "holes"), (5, "ties"), (8, "scaled"), (9, "full"), (16, "holes")])
-def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K, geometry):
+@pytest.mark.parametrize("n,R", [(700, 333), (8192, 8192), (9000, 4100)], ids=["smem", "smem-max", "radix"])
+def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K, geometry, n, R):
     """pld_fused_step_scored (score-only pass + radix top-R + redraw) returns the same kept candidates, in
     the same order, with the same rankings as the staged sample -> score -> select_top pipeline (which the
     tests above pin to the oracle), and its loss / gradient match the oracle."""
     from oracle import listmle_oracle as lo
     from pldepth_b200 import ops
     from tests.golden.make_golden import near_threshold_gt
-    B, H, W, n, R = 3, 40, 36, 700, 333
+    B, H, W = 3, 40, 36
     Hm, Wm = (20, 12) if geometry == "scaled" else (H, W)
     rs = np.random.RandomState(K)
     if geometry == "ties":       # few distinct depths: massive score ties -> tie rule and a big boundary bucket

@@ -223,6 +223,49 @@ __global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* re
     }
 }
 
+// One CTA per image: largest bin t with  sum_{bin >= t} hist >= remaining; extends the key prefix (or, idx_pass, the
+// candidate-index prefix of the exact unordered selection below) by `nbits` bits and clears the histogram for the
+// next pass.  (Folding this into the histogram kernel through a last-CTA ticket was measured 6-7 us SLOWER per
+// pass than this separate 32-CTA launch inside a CUDA graph: the fence after the histogram atomics is the cost.)
+__global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
+                                                       uint64_t* __restrict__ iprefix, int* __restrict__ remaining,
+                                                       int idx_pass, int nbits) {
+  __shared__ unsigned int s_sum[8];
+  const int b = blockIdx.x;
+  unsigned int* h = hist + (size_t)b * SEL_BINS;
+  // thread t owns the 16 bins [4096 - 16(t+1), 4096 - 16t): thread 0 holds the top bins
+  const int hi = SEL_BINS - 16 * threadIdx.x;
+  unsigned int loc[16], tot = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { loc[i] = h[hi - 1 - i]; tot += loc[i]; }
+  // inclusive scan of the per-thread totals (thread 0 = top bins): the owner is the thread whose range contains
+  // the need-th largest candidate
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_sum[wid] = incl;
+  __syncthreads();
+  for (int w = 0; w < wid; ++w) incl += s_sum[w];
+  const unsigned int need = (unsigned int)remaining[b];
+  const unsigned int excl = incl - tot;
+  if ((excl < need && need <= incl) || (threadIdx.x == 255 && incl < need)) {
+    unsigned int above = excl;          // candidates in bins above this thread's range
+    int i = 0;
+    while (i < 15 && above + loc[i] < need) { above += loc[i]; ++i; }
+    const uint64_t bin = (uint64_t)(hi - 1 - i);
+    if (idx_pass) iprefix[b] = (iprefix[b] << nbits) | bin;
+    else prefix[b] = (prefix[b] << nbits) | bin;
+    remaining[b] = (int)(need - above);   // still to take from inside this bin
+  }
+  // clear the histogram for the next pass
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[hi - 1 - i] = 0u;
+}
+
 __global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restrict__ keys, int n, int pass,
                                                        const uint64_t* __restrict__ prefix, unsigned int* __restrict__ hist) {
   __shared__ unsigned int s_h[SEL_BINS];
@@ -241,45 +284,6 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restric
   unsigned int* h = hist + (size_t)b * SEL_BINS;
   for (int i = threadIdx.x; i < SEL_BINS; i += 256)
     if (s_h[i]) atomicAdd(h + i, s_h[i]);
-}
-
-// one CTA per image: largest bin t with  sum_{bin >= t} hist >= remaining
-__global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
-                                                       int* __restrict__ remaining) {
-  __shared__ unsigned int s_sum[256];
-  const int b = blockIdx.x;
-  unsigned int* h = hist + (size_t)b * SEL_BINS;
-  // thread t owns the 16 bins [4096 - 16(t+1), 4096 - 16t): thread 0 holds the top bins
-  const int hi = SEL_BINS - 16 * threadIdx.x;
-  unsigned int loc[16], tot = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { loc[i] = h[hi - 1 - i]; tot += loc[i]; }
-  s_sum[threadIdx.x] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int need = (unsigned int)remaining[b];
-    unsigned int above = 0;
-    int t = 0;
-    while (t < 255 && above + s_sum[t] < need) { above += s_sum[t]; ++t; }
-    s_sum[0] = (unsigned int)t;        // owner thread
-    s_sum[1] = above;                  // candidates in bins above the owner's range
-  }
-  __syncthreads();
-  const int owner = (int)s_sum[0];
-  const unsigned int above0 = s_sum[1];
-  __syncthreads();
-  if ((int)threadIdx.x == owner) {
-    const unsigned int need = (unsigned int)remaining[b];
-    unsigned int above = above0;
-    int i = 0;
-    while (i < 15 && above + loc[i] < need) { above += loc[i]; ++i; }
-    const int bin = hi - 1 - i;
-    prefix[b] = (prefix[b] << 12) | (uint64_t)bin;
-    remaining[b] = (int)(need - above);   // still to take from inside this bin
-  }
-  // clear the histogram for the next pass
-#pragma unroll
-  for (int i = 0; i < 16; ++i) h[hi - 1 - i] = 0u;
 }
 
 constexpr int SC_THREADS = 256;
@@ -364,10 +368,15 @@ __global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t*
   }
 }
 
+// prefix_shift: the unordered selection continues below the 36-bit prefix; when the low 28 key bits are known to be
+// zero (compact float32 score keys) its three key passes are skipped and the prefix is completed here
 __global__ void sel_varying_kernel(const unsigned long long* bits_or, const unsigned long long* bits_and,
-                                   unsigned long long* varying, int B) {
+                                   unsigned long long* varying, int B, uint64_t* prefix, int prefix_shift) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) varying[b] = bits_or[b] ^ bits_and[b];
+  if (b < B) {
+    varying[b] = bits_or[b] ^ bits_and[b];
+    if (prefix_shift) prefix[b] <<= prefix_shift;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -403,45 +412,6 @@ __global__ void __launch_bounds__(256) sel2_hist_kernel(const uint64_t* __restri
   unsigned int* h = hist + (size_t)b * SEL_BINS;
   for (int i = threadIdx.x; i < SEL_BINS; i += 256)
     if (s_h[i]) atomicAdd(h + i, s_h[i]);
-}
-
-// as sel_find_kernel, for a pass of `nbits` bits extending either the key prefix or the index prefix
-__global__ void __launch_bounds__(256) sel2_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
-                                                        uint64_t* __restrict__ iprefix, int* __restrict__ remaining,
-                                                        int idx_pass, int nbits) {
-  __shared__ unsigned int s_sum[256];
-  const int b = blockIdx.x;
-  unsigned int* h = hist + (size_t)b * SEL_BINS;
-  const int hi = SEL_BINS - 16 * threadIdx.x;
-  unsigned int loc[16], tot = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { loc[i] = h[hi - 1 - i]; tot += loc[i]; }
-  s_sum[threadIdx.x] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int need = (unsigned int)remaining[b];
-    unsigned int above = 0;
-    int t = 0;
-    while (t < 255 && above + s_sum[t] < need) { above += s_sum[t]; ++t; }
-    s_sum[0] = (unsigned int)t;
-    s_sum[1] = above;
-  }
-  __syncthreads();
-  const int owner = (int)s_sum[0];
-  const unsigned int above0 = s_sum[1];
-  __syncthreads();
-  if ((int)threadIdx.x == owner) {
-    const unsigned int need = (unsigned int)remaining[b];
-    unsigned int above = above0;
-    int i = 0;
-    while (i < 15 && above + loc[i] < need) { above += loc[i]; ++i; }
-    const uint64_t bin = (uint64_t)(hi - 1 - i);
-    if (idx_pass) iprefix[b] = (iprefix[b] << nbits) | bin;
-    else prefix[b] = (prefix[b] << nbits) | bin;
-    remaining[b] = (int)(need - above);
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) h[hi - 1 - i] = 0u;
 }
 
 __device__ __forceinline__ bool sel2_keep(uint64_t key, uint32_t id, uint64_t tkey, uint32_t tidx) {
@@ -764,7 +734,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   for (int pass = 0; pass < 3; ++pass) {
     sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
     PLD_CHECK_LAUNCH();
-    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, remaining);
+    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, nullptr, remaining, 0, 12);
     PLD_CHECK_LAUNCH();
   }
   dim3 tgrid((unsigned)ntiles, (unsigned)B);
@@ -772,17 +742,20 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   PLD_CHECK_LAUNCH();
   sel_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt, k0, v0, n_surv, bits_or, bits_and);
   PLD_CHECK_LAUNCH();
-  sel_varying_kernel<<<(B + 255) / 256, 256, 0, st>>>(bits_or, bits_and, varying, B);
+  // compact float32 score keys (pld_score.cuh: score_key_f32) carry nothing below bit 32
+  const bool low_bits_zero = (promotion == PLD_PROMOTION_NEP50 && strategy != PLD_STRATEGY_INFORMATION);
+  const int skip_key_passes = (rankings == nullptr && low_bits_zero) ? 1 : 0;
+  sel_varying_kernel<<<(B + 255) / 256, 256, 0, st>>>(bits_or, bits_and, varying, B, prefix, skip_key_passes ? 28 : 0);
   PLD_CHECK_LAUNCH();
 
   if (rankings == nullptr) {
     // 4a. nobody sees the order of the kept lists: refine the selection to the exact cut instead of sorting
     static const int kPass[5][3] = {{0, 16, 12}, {0, 4, 12}, {0, 0, 4}, {1, 11, 12}, {1, 0, 11}};  // idx?, shift, bits
-    for (int p = 0; p < 5; ++p) {
+    for (int p = skip_key_passes ? 3 : 0; p < 5; ++p) {
       sel2_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(k0, v0, n_surv, (size_t)n, kPass[p][0], kPass[p][1],
                                                                          kPass[p][2], prefix, iprefix, shist);
       PLD_CHECK_LAUNCH();
-      sel2_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2]);
+      sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2]);
       PLD_CHECK_LAUNCH();
     }
     sel2_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt);

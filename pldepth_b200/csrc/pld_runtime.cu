@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) select_gather_kernel(const uint32_t* __re
 
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
-                   const unsigned long long* varying, cudaStream_t st);
+                   const unsigned long long* varying, int first_pass, cudaStream_t st);
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
 bool select_small_fits(int n);
 int select_small_init();
@@ -747,7 +747,7 @@ int pld_select_top(pld_ctx* ctx, const double* scores, const float* rankings, in
   if (gx > cap) gx = cap;
   select_keys_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(scores, n, k0, v0);
   PLD_CHECK_LAUNCH();
-  rc = seg_radix_sort(ctx, k0, v0, k1, v1, nullptr, n, (size_t)n, B, hist, nullptr, st);
+  rc = seg_radix_sort(ctx, k0, v0, k1, v1, nullptr, n, (size_t)n, B, hist, nullptr, 0, st);
   if (rc) return rc;
   select_gather_kernel<<<dim3((unsigned)gxr, (unsigned)B), 256, 0, st>>>(v0, rankings, n, K, R, rankings_out, order_out, 0);
   PLD_CHECK_LAUNCH();

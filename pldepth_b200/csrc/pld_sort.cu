@@ -7,14 +7,16 @@
 // order-preserving u64 image of the float64 scores, values the candidate index inside the image.
 // The sort is ascending and stable; the consumer reads the tail of each segment backwards, which
 // yields "score descending, ties: larger candidate index first" (= reversed stable argsort).
+#include <cstdlib>
 #include "pld_common.cuh"
 #include "pld_score.cuh"
 
 namespace pld {
 
 constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // elements per CTA
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 elements per CTA; warp w owns elements [256 w, 256 (w + 1))
 constexpr int RS_BINS = 256;
 
 struct SegInfo {
@@ -22,6 +24,7 @@ struct SegInfo {
   int len_fixed;                      // used when len_dev == nullptr
   size_t stride;                      // elements between consecutive images
   const unsigned long long* varying;  // per-image mask of key bits that differ between live keys (nullable)
+  int first_pass;                     // passes below this one are known to be constant for every image
   __device__ __forceinline__ int len(int b) const { return len_dev ? len_dev[b] : len_fixed; }
   // a pass over a byte in which all live keys agree cannot reorder anything: it is skipped, and the
   // ping-pong parity of an image is the number of passes it really executed
@@ -29,13 +32,21 @@ struct SegInfo {
     return varying != nullptr && ((varying[b] >> (8 * pass)) & 0xFFull) == 0ull;
   }
   __device__ __forceinline__ int parity(int b, int pass) const {  // executed passes before `pass`
-    if (varying == nullptr) return pass & 1;
+    if (varying == nullptr) return (pass - first_pass) & 1;
     const unsigned long long v = varying[b];
     int c = 0;
-    for (int p = 0; p < pass; ++p) c += ((v >> (8 * p)) & 0xFFull) ? 1 : 0;
+    for (int p = first_pass; p < pass; ++p) c += ((v >> (8 * p)) & 0xFFull) ? 1 : 0;
     return c & 1;
   }
 };
+
+// Digit counting of one warp's 32 elements: lanes holding the same digit elect a leader that adds the group size to
+// the warp's counter, so a byte with two or three distinct values (an exponent byte) costs no more than a uniform
+// one.  Returns the number of equal digits in lower lanes (rank inside the group).
+__device__ __forceinline__ int warp_digit_rank(bool on, int d, int lane, unsigned& group) {
+  group = __match_any_sync(0xffffffffu, on ? d : (RS_BINS + lane));   // idle lanes match nobody
+  return __popc(group & ((1u << lane) - 1u));
+}
 
 // per (image, tile) digit histogram -> hist[(b * nblk + tile) * RS_BINS + digit]
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys_a,
@@ -47,7 +58,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
   const int n = seg.len(b);
   const int base = tile * RS_TILE;
   if (base >= n) return;
-  s_h[threadIdx.x] = 0;
+  if (threadIdx.x < RS_BINS) s_h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t* k = (seg.parity(b, pass) ? keys_b : keys_a) + (size_t)b * seg.stride;
   const int shift = pass * 8;
@@ -57,11 +68,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
     if (idx < n) atomicAdd(&s_h[(int)((k[idx] >> shift) & 0xFF)], 1);
   }
   __syncthreads();
-  hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x] = s_h[threadIdx.x];
+  if (threadIdx.x < RS_BINS) hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x] = s_h[threadIdx.x];
 }
 
 // one CTA per image, thread d owns digit d: running prefix over the live tiles (coalesced across
-// digits), then an exclusive scan of the 256 digit totals -> dig_off[b][d]
+// digits, eight tiles in flight), then an exclusive scan of the 256 digit totals -> dig_off[b][d]
 __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist, int* __restrict__ dig_off, SegInfo seg,
                                                           int pass, int nblk) {
   __shared__ int s_tot[RS_BINS];
@@ -71,11 +82,15 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist
   const int live = (n + RS_TILE - 1) / RS_TILE;
   int* h = hist + (size_t)b * nblk * RS_BINS + threadIdx.x;
   int run = 0;
-#pragma unroll 4
-  for (int t = 0; t < live; ++t) {
-    const int c = h[(size_t)t * RS_BINS];
-    h[(size_t)t * RS_BINS] = run;
-    run += c;
+  for (int t0 = 0; t0 < live; t0 += 8) {
+    int c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = (t0 + j < live) ? h[(size_t)(t0 + j) * RS_BINS] : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t0 + j < live) h[(size_t)(t0 + j) * RS_BINS] = run;
+      run += c[j];
+    }
   }
   s_tot[threadIdx.x] = run;
   __syncthreads();
@@ -89,16 +104,17 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist
   dig_off[b * RS_BINS + threadIdx.x] = s_tot[threadIdx.x] - run;
 }
 
-// stable scatter: elements of a tile are ranked round by round (256 consecutive elements per round);
-// inside a round __match_any_sync gives the rank among equal digits of a warp, per-warp digit counts
-// give the rank across warps, running counters carry over rounds.
+// Stable scatter.  Every warp owns 256 consecutive elements of the tile (8 rounds of 32, kept in registers) and
+// ranks them against its own running digit counters: __match_any_sync gives the rank among equal digits of a round,
+// the counter the number of equal digits in the warp's earlier rounds.  Two block barriers per tile: after the
+// counting walk the per-warp counters are turned into global offsets (tile offset of the digit + counts of the
+// lower warps), then every element is written to offset + rank.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
                                                                 uint64_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                                                                 SegInfo seg, int pass, int nblk,
                                                                 const int* __restrict__ hist,
                                                                 const int* __restrict__ dig_off) {
-  __shared__ int s_base[RS_BINS];              // global offset of (digit, this tile) + elements already placed
-  __shared__ int s_wcnt[RS_THREADS / 32][RS_BINS];
+  __shared__ int s_cnt[RS_WARPS][RS_BINS];   // running count while ranking, then the warp's global digit offset
   const int b = blockIdx.y, tile = blockIdx.x;
   if (seg.skip(b, pass)) return;
   const int n = seg.len(b);
@@ -112,44 +128,49 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __rest
   uint32_t* vals_out = (flip ? vals_a : vals_b) + off;
   const int shift = pass * 8;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  s_base[threadIdx.x] = dig_off[b * RS_BINS + threadIdx.x] + hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x];
-#pragma unroll
-  for (int w = 0; w < RS_THREADS / 32; ++w) s_wcnt[w][threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const int idx = base + r * RS_THREADS + threadIdx.x;
-    const bool on = idx < n;
-    uint64_t k = 0;
-    uint32_t v = 0;
-    int d = 0;
-    if (on) {
-      k = keys_in[idx];
-      v = vals_in[idx];
-      d = (int)((k >> shift) & 0xFF);
-    }
-    // lanes past the end use digit 256 + lane so that they match nobody
-    const unsigned m = __match_any_sync(0xffffffffu, on ? d : (256 + lane));
-    const int rank_w = __popc(m & ((1u << lane) - 1u));
-    if (on && rank_w == 0) s_wcnt[wid][d] = __popc(m);
-    __syncthreads();
-    if (on) {
-      int pre = 0;
-      for (int w = 0; w < wid; ++w) pre += s_wcnt[w][d];
-      const int pos = s_base[d] + pre + rank_w;
-      keys_out[pos] = k;
-      vals_out[pos] = v;
-    }
-    __syncthreads();
-    {
-      int t = 0;
+  const int wbase = base + wid * (RS_ITEMS * 32);
+  uint64_t k[RS_ITEMS];
+  int rank[RS_ITEMS];
 #pragma unroll
-      for (int w = 0; w < RS_THREADS / 32; ++w) {
-        t += s_wcnt[w][threadIdx.x];
-        s_wcnt[w][threadIdx.x] = 0;
-      }
-      s_base[threadIdx.x] += t;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    k[r] = (idx < n) ? keys_in[idx] : 0ull;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const bool on = (wbase + r * 32 + lane) < n;
+    const int d = (int)((k[r] >> shift) & 0xFF);
+    unsigned group;
+    const int rw = warp_digit_rank(on, d, lane, group);
+    const int prev = on ? s_cnt[wid][d] : 0;
+    __syncwarp();
+    if (on && rw == 0) s_cnt[wid][d] = prev + __popc(group);
+    __syncwarp();
+    rank[r] = prev + rw;
+  }
+  __syncthreads();
+  if (threadIdx.x < RS_BINS) {
+    // digit d = threadIdx.x: global position of the first element of (this tile, digit d), then per warp
+    int run = dig_off[b * RS_BINS + threadIdx.x] + hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const int c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = run;
+      run += c;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    if (idx < n) {
+      const int d = (int)((k[r] >> shift) & 0xFF);
+      const int pos = s_cnt[wid][d] + rank[r];
+      keys_out[pos] = k[r];
+      vals_out[pos] = vals_in[idx];
+    }
   }
 }
 
@@ -160,13 +181,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __rest
 // hist: int[B * nblk * 256 + B * 256] scratch.
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
-                   const unsigned long long* varying, cudaStream_t st) {
+                   const unsigned long long* varying, int first_pass, cudaStream_t st) {
   if (len_max <= 0) return PLD_OK;
   const int nblk = (len_max + RS_TILE - 1) / RS_TILE;
-  SegInfo seg{len_dev, len_max, stride, varying};
+  SegInfo seg{len_dev, len_max, stride, varying, first_pass};
   int* dig_off = hist + (size_t)B * nblk * RS_BINS;
   dim3 grid((unsigned)nblk, (unsigned)B);
-  for (int pass = 0; pass < 8; ++pass) {
+  for (int pass = first_pass; pass < 8; ++pass) {
     rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(keys, keys_tmp, seg, pass, nblk, hist);
     PLD_CHECK_LAUNCH();
     rs_scan_kernel<<<B, RS_BINS, 0, st>>>(hist, dig_off, seg, pass, nblk);

@@ -21,7 +21,7 @@ int launch_offset_advance(pld_ctx* ctx, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
-                   const unsigned long long* varying, cudaStream_t st);
+                   const unsigned long long* varying, int first_pass, cudaStream_t st);
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
 bool select_small_fits(int n);
 int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
@@ -764,8 +764,9 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
                                                      order_out);
     PLD_CHECK_LAUNCH();
   } else {
-    // 4b. full order of the survivors (ascending, stable); the best R are the tail read backwards
-    rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, varying, st);
+    // 4b. full order of the survivors (ascending, stable LSD radix sort; the four low key bytes are skipped when
+    // they are known to be zero); the best R are the tail read backwards
+    rc = seg_radix_sort(ctx, k0, v0, k1, v1, n_surv, n, (size_t)n, B, rhist, varying, low_bits_zero ? 4 : 0, st);
     if (rc) return rc;
     int go = (R + 255) / 256;
     if (go > per_image_cap) go = per_image_cap;

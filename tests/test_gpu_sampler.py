@@ -386,3 +386,47 @@ def test_numpy_compat_mode_at_scale(cuda_device, strategy, cls):
     else:   # tied scores: same rule on both sides, still identical
         assert np.array_equal(got, want)
     assert np.array_equal(st_after[1], st_want[1]) and st_after[2] == st_want[2]
+
+
+def _want_order(scores, R):
+    return np.argsort(scores, kind="stable")[::-1][:R].astype(np.int32)
+
+
+@pytest.mark.parametrize("kind", ["all-equal", "two-values", "dense-f32", "wide-f64", "clustered"])
+@pytest.mark.parametrize("n,R", [(20000, 7000), (300000, 299999)])
+def test_top_selection_on_adversarial_scores(cuda_device, kind, n, R):
+    """The segmented radix sort behind pld_select_top (more than 8192 candidates per image) on awkward score
+    distributions: all equal, two values (two-valued digit bytes), one binade, 600 decades, two far-apart clusters.
+    Result = reversed stable argsort (sampling.py:169, 208, 239)."""
+    from pldepth_b200 import ops
+    rs = np.random.RandomState(n % 1000 + len(kind))
+    B = 2
+    if kind == "all-equal":
+        sc = np.full((B, n), -3.25)
+    elif kind == "two-values":
+        sc = rs.choice([-1000.5, 0.125], size=(B, n))
+    elif kind == "dense-f32":
+        sc = rs.rand(B, n).astype(np.float32).astype(np.float64) * 0.5 + 0.5
+    elif kind == "wide-f64":
+        sc = rs.standard_normal((B, n)) * 10.0 ** rs.randint(-300, 300, size=(B, n))
+    else:
+        sc = np.where(rs.rand(B, n) < 0.5, -1000.0, 0.0) - rs.rand(B, n) * 1e-3
+    cand = torch.arange(B * n, dtype=torch.float32, device=cuda_device).reshape(B, n, 1, 1).repeat(1, 1, 1, 2)
+    top, order = ops.select_top(torch.from_numpy(sc).to(cuda_device), cand, R, want_order=True)
+    ops.check_status(cuda_device)
+    order_h = order.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(order_h[b], _want_order(sc[b], R))
+    assert torch.equal(top[..., 0, 0], (order.long() + torch.arange(B, device=cuda_device)[:, None] * n).float())
+
+
+def test_top_selection_very_long_segment(cuda_device):
+    """1.6 M candidates in one image (hundreds of tiles per image in the segmented sort)."""
+    from pldepth_b200 import ops
+    n, R = 1_600_000, 1_000_000
+    rs = np.random.RandomState(3)
+    sc = np.round(rs.standard_normal((1, n)), 3)          # plenty of ties
+    cand = torch.zeros((1, n, 1, 2), dtype=torch.float32, device=cuda_device)
+    _, order = ops.select_top(torch.from_numpy(sc).to(cuda_device), cand, R, want_order=True)
+    ops.check_status(cuda_device)
+    assert np.array_equal(order.cpu().numpy()[0], _want_order(sc[0], R))

@@ -109,6 +109,28 @@ __device__ __forceinline__ void sort_desc_regs(uint64_t (&key)[K], uint32_t (&pa
 #undef PLD_CE
 }
 
+// The same networks on bare depths (descending), two FMNMX per comparator: enough for the scoring pass, whose result
+// depends on the ordered depths only (tied depths are interchangeable there).
+template <int K>
+__device__ __forceinline__ void sort_desc_floats(float (&g)[K]) {
+#define PLD_CEF(i, j)                                  \
+  do {                                                 \
+    const float hi_ = fmaxf(g[i], g[j]), lo_ = fminf(g[i], g[j]); \
+    g[i] = hi_; g[j] = lo_;                            \
+  } while (0)
+  if constexpr (K == 5) {
+    PLD_CEF(0, 1); PLD_CEF(3, 4); PLD_CEF(2, 4); PLD_CEF(2, 3); PLD_CEF(1, 4);
+    PLD_CEF(0, 3); PLD_CEF(0, 2); PLD_CEF(1, 3); PLD_CEF(1, 2);
+  } else {
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+#pragma unroll
+      for (int j = i; j > 0; --j) PLD_CEF(j - 1, j);
+    }
+  }
+#undef PLD_CEF
+}
+
 // ListMLE on K scores already in sorted (label-descending) order, all in registers.
 // nll = sum_k log(S_k) - (s_k - m),  S_k = sum_{j>=k} exp(s_j - m)   (reverse cumsum)
 // g_k = exp(s_k - m) * sum_{i<=k} 1/S_i - 1

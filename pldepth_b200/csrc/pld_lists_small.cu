@@ -193,7 +193,15 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
 #pragma unroll
           for (int k = 0; k < K; ++k) so[k] = sel[k];
         }
-        if (SRC == SRC_PHILOX_TAB) {
+        if (SCORE && SRC == SRC_PHILOX_TAB) {
+          // scoring pass: only the ordered depths matter (no pixel index, no prediction)
+          float gs[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) gs[k] = gs_layout ? t[k].x : t[k].y;
+          sort_desc_floats<K>(gs);
+#pragma unroll
+          for (int k = 0; k < K; ++k) key[k] = (uint64_t)float_to_ordered(gs[k]) << 32;
+        } else if (SRC == SRC_PHILOX_TAB) {
           // per-image lookup table built by prep_build_kernel: one 8-byte gather per draw
           if (gs_layout) {
             // entry j = (gt, pred) of the j-th valid pixel (full mask: of pixel j); the prediction rides through

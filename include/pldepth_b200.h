@@ -211,8 +211,9 @@ int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float
 
 /* Same step for the score-based strategies (Masked / Thresholded / InformationScore,
  * sampling.py:157-169, 190-208, 218-239): n = int(R * factor) Philox candidate lists per image are drawn
- * and scored (only the 8-byte ordered score is stored), a radix top-R selection + segmented radix sort
- * orders the best R by score descending (ties: larger candidate index first), and the kept lists are
+ * and scored (only the 8-byte ordered score is stored), the best R are ordered by score descending (ties:
+ * larger candidate index first) -- one shared-memory sort per image up to 8192 candidates, radix top-R
+ * selection + segmented radix sort above that -- and the kept lists are
  * REDRAWN from their Philox list ids inside the fused kernel that emits rankings / loss / gradient.
  * Results equal pld_sample_lists_philox(n) -> pld_score_lists -> pld_select_top(R) -> pld_listmle_fwd_bwd.
  * pred / loss / grad may be NULL (sampler only: rankings and order_out).  ranking_size 1..16.

@@ -101,21 +101,11 @@ class FusedPLStep(object):
                                             c_void_p(None), p(buf["grad"]), stream))
             self.step_index += 1
             return buf
-        if True:
-            # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
-            check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
-                                     self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
-                                     p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),
-                                     p(buf["grad"]), stream))
-            self.step_index += 1
-            return buf
-        check(lib.pld_mask_compact(ctx.handle, p(mask), B, Hm, Wm, H, W, p(buf["valid_flat"]), p(buf["n_valid"]),
-                                   stream))
-        check(lib.pld_fused_sample_loss_bwd(ctx.handle, p(gt), p(buf["valid_flat"]), p(buf["n_valid"]), p(pred), B,
-                                            H * W, Hm * Wm, self.K, self.R, self.seed, self.step_index,
-                                            self.image_base, ctypes.c_float(scale), p(buf["rankings"]),
-                                            p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None), p(buf["grad"]), 0,
-                                            stream))
+        # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
+        check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
+                                 self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
+                                 p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),
+                                 p(buf["grad"]), stream))
         self.step_index += 1
         return buf
 

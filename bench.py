@@ -37,10 +37,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5s", "C5"])
-    ap.add_argument("--sets", type=int, default=4, help="rotating input/output buffer sets (> L2 in total)")
+    ap.add_argument("--sets", type=int, default=6, help="rotating input/output buffer sets (> L2 in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for cpu_baseline")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--lanes", type=int, default=None,
+                    help="independent batches in flight on separate streams (each lane has its own context, hence "
+                         "its own lookup tables): the HBM-bound table build of one step overlaps the list kernel "
+                         "of the previous one.  1 = strictly sequential steps.  Default: 3 (1 for launch-bound "
+                         "workloads of fewer than 100 000 lists per step)")
     ap.add_argument("--no-emit", action="store_true", help="do not materialise the rankings (what a fused training "
                                                            "step needs; the default emits them like the reference)")
     ap.add_argument("--hole", type=float, default=0.0, help="fraction of each mask zeroed (default: all-ones mask)")
@@ -234,31 +239,58 @@ def run_b200(args):
                          mask=torch.from_numpy(mask_h).to(dev),
                          pred=torch.from_numpy(np.roll(pred_h, s, axis=0)).to(dev),
                          out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev, emit_rankings=not args.no_emit)))
+    from pldepth_b200._lib import Context
     step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B, emit_rankings=not args.no_emit)
+    # lanes: consecutive steps work on different buffer sets and do not depend on each other, so `lanes` of them
+    # are kept in flight on separate streams.  Lane 0 is the plain step on the current stream.
+    want_lanes = args.lanes if args.lanes is not None else (3 if L >= 100000 else 1)
+    n_lanes = 1 if args.graph else max(1, min(want_lanes, n_sets))
+    while n_sets % n_lanes:      # a buffer set must always be used by the same lane (stream order protects it)
+        n_lanes -= 1
+    lane_steps, lane_streams = [step], [torch.cuda.current_stream(dev)]
+    for l in range(1, n_lanes):
+        lane_steps.append(FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B,
+                                      emit_rankings=not args.no_emit, context=Context(local_rank),
+                                      first_step=l << 24))
+        lane_streams.append(torch.cuda.Stream(dev))
 
     pending = []
 
-    def one_step(i):
+    def one_step(i, lanes=1):
         s = sets[i % n_sets]
-        out = step.run(s["gt"], s["mask"], s["pred"], out=s["out"])
-        if world > 1:
-            # the path's only exchange: one f64 per step.  Nothing downstream of the step depends on it
-            # (the gradient already carries the global 1/L), so it is issued asynchronously and overlaps
-            # the next step; every reduction is waited for before the timed region closes.
-            pending.append(dist.all_reduce(out["loss_sum"], async_op=True))
-            if len(pending) > n_sets - 1:
-                pending.pop(0).wait()
+        lane = i % lanes
+        with torch.cuda.stream(lane_streams[lane]):
+            out = lane_steps[lane].run(s["gt"], s["mask"], s["pred"], out=s["out"])
+            if world > 1:
+                # the path's only exchange: one f64 per step.  Nothing downstream of the step depends on it
+                # (the gradient already carries the global 1/L), so it is issued asynchronously and overlaps
+                # the next step; every reduction is waited for before the timed region closes.
+                pending.append(dist.all_reduce(out["loss_sum"], async_op=True))
+                if len(pending) > n_sets - 1:
+                    pending.pop(0).wait()
         return out
+
+    def fork_lanes(ev):
+        for st in lane_streams[1:]:
+            st.wait_event(ev)
+
+    def join_lanes():
+        cur = torch.cuda.current_stream(dev)
+        for st in lane_streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
 
     def drain():
         while pending:
             pending.pop(0).wait()
 
     for i in range(max(3, args.warmup)):
-        one_step(i)
+        one_step(i, n_lanes)
     drain()
     torch.cuda.synchronize()
-    step.check(dev)
+    for ls in lane_steps:
+        ls.check(dev)
 
     graphs = None
     if args.graph and world == 1:
@@ -280,6 +312,22 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- dominant kernel alone: the library records CUDA events around the list kernel of every
+    # step (pld_ctx_kernel_timing) on its launch stream, over a strictly sequential pass of the same steps
+    # (one lane: nothing else runs beside the kernel), taken BEFORE the timed region so that the power
+    # state left behind by the multi-lane burst cannot leak into it -----
+    ctx = Context.current(local_rank)
+    n_k = max(5, min(args.steps, 50))
+    ctx.kernel_timing(n_k)
+    for i in range(n_k):
+        one_step(i)
+    drain()
+    torch.cuda.synchronize()
+    kms = ctx.kernel_times(n_k)
+    ctx.kernel_timing(0)
+    kms = sorted(kms)
+    k_ms = sum(kms) / len(kms)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _lib.launch_count()
@@ -287,11 +335,13 @@ def run_b200(args):
     barrier()
     sampler.rows.clear()
     e0.record()
+    fork_lanes(e0)
     for i in range(args.steps):
         if graphs is not None:
             graphs[i % n_sets].replay()
         else:
-            one_step(i)
+            one_step(i, n_lanes)
+    join_lanes()
     drain()
     e1.record()
     barrier()
@@ -311,27 +361,14 @@ def run_b200(args):
         if graphs is not None:
             graphs[i % n_sets].replay()
         else:
-            one_step(i)
+            one_step(i, n_lanes)
     drain()
     torch.cuda.synchronize()
     sampler.stop_flag.set()
     sampler.join(timeout=3)
-    step.check(dev)
+    for ls in lane_steps:
+        ls.check(dev)
 
-    # ---- dominant kernel alone: the library records CUDA events around the list kernel of every
-    # step (pld_ctx_kernel_timing) on its launch stream, over a second pass of the same steps -----
-    from pldepth_b200._lib import Context
-    ctx = Context.current(local_rank)
-    n_k = max(5, min(args.steps, 50))
-    ctx.kernel_timing(n_k)
-    for i in range(n_k):
-        one_step(i)
-    drain()
-    torch.cuda.synchronize()
-    kms = ctx.kernel_times(n_k)
-    ctx.kernel_timing(0)
-    kms = sorted(kms)
-    k_ms = sum(kms) / len(kms)
     peak, peak_src = peaks()
     abytes = algorithmic_bytes(B, HW, L, K)
     achieved = abytes / (k_ms * 1e-3) / 1e9
@@ -395,7 +432,9 @@ def run_b200(args):
                        "lists_per_step": L * world, "sharding": "per image, %d GPU(s)" % world,
                        "cache": "rotating %d input/output buffer sets of %.0f MB each (> 126 MB L2), no reuse "
                                 "between consecutive steps" % (n_sets, abytes / 1e6),
-                       "cuda_graph": bool(graphs)},
+                       "cuda_graph": bool(graphs),
+                       "lanes": "%d independent batches in flight on separate streams (own lookup tables each); "
+                                "roofline.kernel_ms is timed in a separate sequential pass" % n_lanes},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "lists_small_kernel<K,PHILOX_TAB,LOSS> (fused sample+order+emit+gather+loss+bwd)",
                          "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src},

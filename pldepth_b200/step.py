@@ -18,17 +18,21 @@ from ._lib import Context, check, c_void_p
 class FusedPLStep(object):
     def __init__(self, ranking_size, rankings_per_image, seed=0, emit_rankings=True, global_batch=None,
                  image_base=0, strategy="purely", candidate_factor=None, threshold=0.03, equality_penalty=-1000,
-                 promotion="nep50"):
+                 promotion="nep50", context=None, first_step=0):
         """``strategy``: 'purely' (core sampler, exactly R lists/image -- the headline path) or one of
         'masked' / 'thresholded' / 'information' (R best of int(R * candidate_factor) candidates, default
-        factors 1.5 / 1.5 / 5 as in sampling.py:157,190,218)."""
+        factors 1.5 / 1.5 / 5 as in sampling.py:157,190,218).
+        ``context``: a private ``_lib.Context`` (own scratch and lookup tables) instead of the thread's; steps of
+        independent batches that run concurrently on different streams need one each.  ``first_step`` is the Philox
+        offset of the first call (concurrent lanes take disjoint ranges)."""
         self.K = int(ranking_size)
         self.R = int(rankings_per_image)
         self.seed = int(seed)
         self.emit_rankings = bool(emit_rankings)
         self.global_batch = global_batch
         self.image_base = int(image_base)
-        self.step_index = 0
+        self.step_index = int(first_step)
+        self._ctx = context
         self._buf = None
         if strategy not in ("purely", "masked", "thresholded", "information"):
             raise ValueError("unknown strategy %r" % (strategy,))
@@ -68,7 +72,7 @@ class FusedPLStep(object):
         B, H, W = gt.shape[0], gt.shape[1], gt.shape[2]
         Hm, Wm = mask.shape[1], mask.shape[2]
         buf = out if out is not None else self._buffers(B, H, W, Hm, Wm, dev)
-        ctx = Context.current(dev.index or 0)
+        ctx = self._ctx if self._ctx is not None else Context.current(dev.index or 0)
         lib = ctx.lib
         stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         gb = self.global_batch if self.global_batch else B
@@ -115,7 +119,7 @@ class FusedPLStep(object):
         copying into the same gt / mask / pred tensors.  Returns (graph, output buffers).  While a captured step
         is in use, other Philox calls on this thread's context share (and advance) the same device counter."""
         dev = gt.device
-        ctx = Context.current(dev.index or 0)
+        ctx = self._ctx if self._ctx is not None else Context.current(dev.index or 0)
         ctx.device_offset(True, self.step_index)
         self.run(gt, mask, pred, out=out)                 # warm-up: scratch allocation happens outside capture
         torch.cuda.synchronize(dev)
@@ -137,6 +141,9 @@ class FusedPLStep(object):
         )
 
     def check(self, dev):
+        """Synchronise the current stream and raise on the status bits of this step's context."""
+        if self._ctx is not None:
+            return self._ctx.raise_on_status(torch.cuda.current_stream(dev).cuda_stream)
         return ops.check_status(dev)
 
 

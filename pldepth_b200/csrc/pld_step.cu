@@ -532,6 +532,34 @@ __global__ void __launch_bounds__(256) vj_expand_kernel(const float* __restrict_
 
 using namespace pld;
 
+// Passes 1-2 of both fused steps: valid pixels counted per chunk while `grad` is zeroed, then the per-image lookup
+// tables (layouts: see prep_build_kernel).
+static int launch_prep(const float* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
+                       int* counts, float2* table, size_t tstride, int32_t* nv, int32_t* vj_flat, float* grad_valid,
+                       float* grad, cudaStream_t st) {
+  const int HW = H * W, Nm = Hm * Wm;
+  const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
+  dim3 grid((unsigned)nchunks, (unsigned)B);
+  const size_t gtotal = (size_t)B * HW;
+  float4* g4 = nullptr;
+  size_t n4 = 0;
+  int tail = 0;
+  if (grad != nullptr) {
+    PLD_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
+    g4 = reinterpret_cast<float4*>(grad);
+    n4 = gtotal / 4;
+    tail = (int)(gtotal - n4 * 4);
+  }
+  prep_count_kernel<<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
+  PLD_CHECK_LAUNCH();
+  const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
+  const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
+  prep_build_kernel<<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
+                                                table, tstride, nv, vj_flat, grad_valid);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
 extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
                               int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
                               float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
@@ -566,24 +594,9 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   rc = ctx->ensure_partials(per_image_cap * B + B);
   if (rc) return rc;
 
-  dim3 grid((unsigned)nchunks, (unsigned)B);
   const size_t gtotal = (size_t)B * HW;
-  float4* g4 = nullptr;
-  size_t n4 = 0;
-  int tail = 0;
-  if (grad != nullptr) {
-    PLD_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
-    g4 = reinterpret_cast<float4*>(grad);
-    n4 = gtotal / 4;
-    tail = (int)(gtotal - n4 * 4);
-  }
-  prep_count_kernel<<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
-  PLD_CHECK_LAUNCH();
-  const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
-  const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
-  prep_build_kernel<<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv, vj_flat, grad_valid);
-  PLD_CHECK_LAUNCH();
+  rc = launch_prep(mask, gt, pred, B, Hm, Wm, H, W, counts, table, tstride, nv, vj_flat, grad_valid, grad, st);
+  if (rc) return rc;
   if (n == 0) {
     PLD_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if (loss_sum) PLD_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
@@ -691,24 +704,9 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   if (rc) return rc;
 
   // 1. valid pixels + zeroed grad + lookup tables (as pld_fused_step)
-  dim3 pgrid((unsigned)nchunks, (unsigned)B);
   const size_t gtotal = (size_t)B * HW;
-  float4* g4 = nullptr;
-  size_t n4 = 0;
-  int tail = 0;
-  if (grad != nullptr) {
-    PLD_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
-    g4 = reinterpret_cast<float4*>(grad);
-    n4 = gtotal / 4;
-    tail = (int)(gtotal - n4 * 4);
-  }
-  prep_count_kernel<<<pgrid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
-  PLD_CHECK_LAUNCH();
-  const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
-  const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
-  prep_build_kernel<<<pgrid, PC_THREADS, 0, st>>>(mask, gt, pred ? pred : gt, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks,
-                                                 counts, table, tstride, nv, nullptr, nullptr);
-  PLD_CHECK_LAUNCH();
+  rc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, counts, table, tstride, nv, nullptr, nullptr, grad, st);
+  if (rc) return rc;
   if (strategy == PLD_STRATEGY_INFORMATION) {
     gt_minmax_step_kernel<<<B, 1024, 0, st>>>(gt, HW, minmax);
     PLD_CHECK_LAUNCH();

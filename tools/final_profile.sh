@@ -7,4 +7,4 @@ python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_final.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:lists_small -c 2 -o gpurun_out/r01_fused_final -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-tail -2 gpurun_out/pytest.log gpurun_out/smoke.log
+tail -n 2 gpurun_out/pytest.log; tail -n 2 gpurun_out/smoke.log

@@ -230,6 +230,42 @@ __global__ void __launch_bounds__(256) k_philox(float* out) {
   if (acc == 0x12345u) out[0] = 1.f;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Memory skeleton of one config-2 step (B = 32 images of 448 x 448, K = 5, R = 100 000 lists per image): per list FIVE
+// divergent 8-byte table gathers, FIVE divergent float reductions into the image's map and one 40-byte ranking row --
+// exactly the list kernel's global-memory operations, same grid, NO sampling / ordering / loss arithmetic (indices
+// come from a two-instruction LCG).  Its time is the floor of any list-major kernel with this interface.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K, bool EMIT>
+__global__ void __launch_bounds__(256) k_step_skeleton(const float2* __restrict__ table, float* __restrict__ grad,
+                                                       float2* __restrict__ rows, uint32_t region, int n) {
+  const int b = blockIdx.y;
+  const float2* tab = table + (size_t)b * region;
+  float* g = grad + (size_t)b * region;
+  uint32_t x = (blockIdx.y * gridDim.x + blockIdx.x) * 256u + threadIdx.x + 12345u;
+  for (int l = blockIdx.x * 256 + threadIdx.x; l < n; l += gridDim.x * 256) {
+    uint32_t idx[K];
+    float2 t[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      x = x * 1664525u + 1013904223u;
+      idx[k] = (uint32_t)(((uint64_t)x * region) >> 32);
+      t[k] = __ldg(tab + idx[k]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += t[k].x * t[k].y;
+#pragma unroll
+    for (int k = 0; k < K; ++k) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g + idx[k]), "f"(s * 1e-9f) : "memory");
+    if (EMIT) {
+      float2* r = rows + ((size_t)b * n + l) * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[k] = make_float2((float)idx[k], t[k].x);
+    }
+  }
+}
+
 static int g_sms = 148;
 static double g_clock_ghz = 1.9;
 
@@ -288,6 +324,19 @@ int main() {
     timeit("red_tma_bulk16B_image_major", ops, [&] { k_red_tma<false><<<grid, 256>>>(map, REGION, NREG); });
     timeit("red_mixed_tma+lsu_image_major", ops, [&] { k_red_tma<true><<<grid, 256>>>(map, REGION, NREG); });
     timeit("gather4B_then_red_pairs(ops=pairs)", ops, [&] { k_gather_then_red<<<grid, 256>>>(map, map + (size_t)REGION * NREG, REGION, NREG); });
+  }
+
+  {
+    // memory skeleton of the headline step (see k_step_skeleton)
+    const int B = 32, R = 100000, K = 5;
+    float2* rows; CK(cudaMalloc(&rows, sizeof(float2) * (size_t)B * R * K));
+    dim3 sg((unsigned)((g_sms * 8 + B - 1) / B), (unsigned)B);
+    const double lists = (double)B * R;
+    timeit("step_skeleton_C2_5gathers_5reds_rows(ops=lists)", lists,
+           [&] { k_step_skeleton<5, true><<<sg, 256>>>((const float2*)map, map + 2 * (size_t)REGION * NREG, rows, REGION, R); });
+    timeit("step_skeleton_C2_5gathers_5reds(ops=lists)", lists,
+           [&] { k_step_skeleton<5, false><<<sg, 256>>>((const float2*)map, map + 2 * (size_t)REGION * NREG, rows, REGION, R); });
+    CK(cudaFree(rows));
   }
   const int smem = 200 * 1024;
   CK(cudaFuncSetAttribute(k_gather_smem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

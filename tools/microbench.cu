@@ -337,6 +337,11 @@ int main() {
     timeit("step_skeleton_C2_5gathers_5reds(ops=lists)", lists,
            [&] { k_step_skeleton<5, false><<<sg, 256>>>((const float2*)map, map + 2 * (size_t)REGION * NREG, rows, REGION, R); });
     CK(cudaFree(rows));
+    // config 3: B = 16, K = 50, R = 50 000 (40 M points)
+    const int B3 = 16, R3 = 50000;
+    dim3 sg3((unsigned)((g_sms * 8 + B3 - 1) / B3), (unsigned)B3);
+    timeit("step_skeleton_C3_50gathers_50reds(ops=lists)", (double)B3 * R3,
+           [&] { k_step_skeleton<50, false><<<sg3, 256>>>((const float2*)map, map + 2 * (size_t)REGION * NREG, nullptr, REGION, R3); });
   }
   const int smem = 200 * 1024;
   CK(cudaFuncSetAttribute(k_gather_smem<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -18,6 +18,7 @@ struct ListParams {
   size_t table_stride;
   float* rank_out;             // [B, n, K, 2] nullable
   uint64_t* score_keys;        // [B, n] ordered scores (score mode of the small kernel)
+  unsigned int* sel_hist;      // [B, 4096] nullable: histogram of the top 12 key bits (first pass of the radix top-R)
   ScoreCfg score_cfg;
   // optional indirection: list l of image b redraws candidate list_map[b*map_stride + l]
   const uint32_t* list_map;

@@ -42,7 +42,13 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
   __shared__ float2 s_stage[8 * 32 * STRIDE];
+  // scoring pass: the first histogram of the radix top-R selection (top 12 key bits) is taken on the fly
+  __shared__ unsigned int s_hist[SCORE ? 4096 : 1];
   const int b = blockIdx.y;
+  if (SCORE && P.sel_hist != nullptr) {
+    for (int i = threadIdx.x; i < 4096; i += 256) s_hist[i] = 0u;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t map_off = (size_t)b * (size_t)P.HW;
   const float* __restrict__ gt = P.gt + map_off;
@@ -252,7 +258,14 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
                                 : score_regs<double, K>(lab, P.score_cfg, b);
           const bool f32_exact = P.score_cfg.promotion == PLD_PROMOTION_NEP50 &&
                                  P.score_cfg.strategy != PLD_STRATEGY_INFORMATION;
-          if (active) P.score_keys[list_id] = f32_exact ? score_key_f32((float)sc) : score_key(sc);
+          const uint64_t skey = f32_exact ? score_key_f32((float)sc) : score_key(sc);
+          if (active) P.score_keys[list_id] = skey;
+          if (P.sel_hist != nullptr) {
+            // lanes with the same bin elect one to add the group size (scores cluster in a few bins)
+            const uint32_t bin = (uint32_t)(skey >> 52);
+            const unsigned grp = __match_any_sync(0xffffffffu, active ? bin : (4096u + (uint32_t)lane));
+            if (active && lane == __ffs((int)grp) - 1) atomicAdd(&s_hist[bin], (unsigned int)__popc(grp));
+          }
           continue;
         }
         if (P.rank_out != nullptr) {
@@ -307,6 +320,12 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     }
   }
   if (bad) atomicOr(P.status, bad);
+  if (SCORE && P.sel_hist != nullptr) {
+    __syncthreads();
+    unsigned int* h = P.sel_hist + (size_t)b * 4096;
+    for (int i = threadIdx.x; i < 4096; i += 256)
+      if (s_hist[i]) atomicAdd(h + i, s_hist[i]);
+  }
   if (LOSS) block_loss_epilogue(local, P.partials, P.ticket, P.scale, P.loss, P.loss_sum);
 }
 

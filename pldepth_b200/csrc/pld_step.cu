@@ -236,9 +236,16 @@ __global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* re
 // pass than this separate 32-CTA launch inside a CUDA graph: the fence after the histogram atomics is the cost.)
 __global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict__ hist, uint64_t* __restrict__ prefix,
                                                        uint64_t* __restrict__ iprefix, int* __restrict__ remaining,
-                                                       int idx_pass, int nbits) {
+                                                       int idx_pass, int nbits, const int* __restrict__ n_surv, int R,
+                                                       int last) {
   __shared__ unsigned int s_sum[8];
   const int b = blockIdx.x;
+  if (n_surv != nullptr && n_surv[b] == R) {
+    // exact unordered selection of an image whose survivors are exactly the R kept lists (no ties on the boundary):
+    // its histograms were skipped; the final cut (key, index) = (0, 0) keeps every survivor
+    if (last && threadIdx.x == 0) { prefix[b] = 0ull; iprefix[b] = 0ull; }
+    return;
+  }
   unsigned int* h = hist + (size_t)b * SEL_BINS;
   // thread t owns the 16 bins [4096 - 16(t+1), 4096 - 16t): thread 0 holds the top bins
   const int hi = SEL_BINS - 16 * threadIdx.x;
@@ -396,12 +403,14 @@ __global__ void sel_varying_kernel(const unsigned long long* bits_or, const unsi
 __global__ void __launch_bounds__(256) sel2_hist_kernel(const uint64_t* __restrict__ keys_s, const uint32_t* __restrict__ vals_s,
                                                         const int* __restrict__ n_surv, size_t stride, int idx_pass,
                                                         int shift, int nbits, const uint64_t* __restrict__ prefix,
-                                                        const uint64_t* __restrict__ iprefix, unsigned int* __restrict__ hist) {
+                                                        const uint64_t* __restrict__ iprefix, unsigned int* __restrict__ hist,
+                                                        int R) {
   __shared__ unsigned int s_h[SEL_BINS];
   const int b = blockIdx.y;
+  const int n = n_surv[b];
+  if (n == R) return;   // no boundary ties in this image: every survivor is kept (sel_find_kernel opens the cut)
   for (int i = threadIdx.x; i < SEL_BINS; i += 256) s_h[i] = 0u;
   __syncthreads();
-  const int n = n_surv[b];
   const uint64_t* k = keys_s + (size_t)b * stride;
   const uint32_t* v = vals_s + (size_t)b * stride;
   const uint64_t pre = prefix[b], ipre = iprefix[b];
@@ -723,10 +732,18 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
   P.score_keys = keys;
   P.score_cfg = make_score_cfg(minmax, strategy, threshold, equality_penalty, promotion);
+  const bool radix_select = !select_small_fits(n);
+  if (radix_select) {
+    // the scoring pass also takes the first histogram of the selection (top 12 key bits)
+    sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and, iprefix);
+    PLD_CHECK_LAUNCH();
+    P.sel_hist = shist;
+  }
   rc = launch_lists_small_score(P, ctx->num_sms, st);
   if (rc) return rc;
+  P.sel_hist = nullptr;
 
-  if (select_small_fits(n)) {
+  if (!radix_select) {
     // 3'. few candidates per image (the sizes the reference runs): one shared-memory sort per image
     rc = select_small(keys, nullptr, n, (size_t)n, B, R, rankings == nullptr, order, order_out, st);
     if (rc) return rc;
@@ -734,12 +751,12 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   // 3. radix top-R selection -> survivors in candidate order
   int gsel = (n + 255) / 256;
   if (gsel > per_image_cap) gsel = per_image_cap;
-  sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and, iprefix);
-  PLD_CHECK_LAUNCH();
   for (int pass = 0; pass < 3; ++pass) {
-    sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
-    PLD_CHECK_LAUNCH();
-    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, nullptr, remaining, 0, 12);
+    if (pass > 0) {   // pass 0 was histogrammed by the scoring kernel
+      sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
+      PLD_CHECK_LAUNCH();
+    }
+    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, nullptr, remaining, 0, 12, nullptr, 0, 0);
     PLD_CHECK_LAUNCH();
   }
   dim3 tgrid((unsigned)ntiles, (unsigned)B);
@@ -758,9 +775,10 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     static const int kPass[5][3] = {{0, 16, 12}, {0, 4, 12}, {0, 0, 4}, {1, 11, 12}, {1, 0, 11}};  // idx?, shift, bits
     for (int p = skip_key_passes ? 3 : 0; p < 5; ++p) {
       sel2_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(k0, v0, n_surv, (size_t)n, kPass[p][0], kPass[p][1],
-                                                                         kPass[p][2], prefix, iprefix, shist);
+                                                                         kPass[p][2], prefix, iprefix, shist, R);
       PLD_CHECK_LAUNCH();
-      sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2]);
+      sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2], n_surv, R,
+                                         p == 4 ? 1 : 0);
       PLD_CHECK_LAUNCH();
     }
     sel2_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt);

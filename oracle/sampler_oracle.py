@@ -2,7 +2,7 @@
 
 Follows /root/reference/pldepth/data/sampling.py (cited per function as ``sampling.py:L``)
 and pldepth/data/depth_utils.py:5-21 (``get_depth_relation``).  Pinned bit-exactly against
-the unmodified reference file run in the build container (tests/test_oracle_vs_reference.py
+the unmodified reference file run in the build container (tests/test_oracle_sampler.py
 and the committed tests/golden/sampler_*.npz).
 
 Two executions of the same algorithm are provided:

@@ -430,3 +430,36 @@ def test_top_selection_very_long_segment(cuda_device):
     _, order = ops.select_top(torch.from_numpy(sc).to(cuda_device), cand, R, want_order=True)
     ops.check_status(cuda_device)
     assert np.array_equal(order.cpu().numpy()[0], _want_order(sc[0], R))
+
+
+@pytest.mark.parametrize("strategy", ["thresholded", "information"])
+def test_scored_step_at_config2_scale(cuda_device, strategy):
+    """BASELINE config-2 shapes per image (448 x 448, K = 5, R = 100 000; 150 000 / 500 000 candidates): the one-call
+    scored step still equals the staged sample -> score -> select pipeline bit for bit, and the unordered selection
+    keeps the same set.  Exercises many selection tiles, multi-tile radix passes and the tie-free shortcut."""
+    from pldepth_b200 import ops, synth
+    B, H, W, K, R = 2, 448, 448, 5, 100000
+    n = int(R * (1.5 if strategy == "thresholded" else 5))
+    gt = np.stack([synth.depth_map(H, W, 40 + b) for b in range(B)])
+    if strategy == "thresholded":
+        gt[1] = np.round(gt[1] * 64) / 64 + 0.01          # an image whose scores tie massively
+    mask = np.stack([synth.valid_mask(H, W, 50 + b, 0.1 * b) for b in range(B)])
+    gt_d, mask_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(mask).to(cuda_device)
+    pred_d = torch.randn((B, H, W, 1), device=cuda_device)
+    out = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, "nep50", seed=9, offset=1,
+                                want_order=True)
+    vf, nv = ops.mask_compact(mask_d, H, W)
+    cand, _ = ops.sample_lists_philox(gt_d, vf, nv, K, n, 9, 1, 0)
+    mm = ops.gt_minmax(gt_d) if strategy == "information" else None
+    scores = ops.score_lists(cand, strategy, 0.03, -1000, "nep50", mm)
+    top, order = ops.select_top(scores, cand, R, want_order=True)
+    ops.check_status(cuda_device)
+    assert torch.equal(out["order"], order) and torch.equal(out["rankings"], top)
+    # the staged order itself against NumPy's reversed stable argsort
+    sc_h = scores.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(order[b].cpu().numpy(), _want_order(sc_h[b], R))
+    out3 = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, "nep50", seed=9, offset=1,
+                                 want_rankings=False, want_order=True)
+    assert torch.equal(out3["order"], torch.sort(order, dim=1).values)
+    assert abs(out3["loss"].item() - out["loss"].item()) <= 1e-6 * abs(out["loss"].item())

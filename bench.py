@@ -436,7 +436,10 @@ def run_b200(args):
                        "lanes": "%d independent batches in flight on separate streams (own lookup tables each); "
                                 "roofline.kernel_ms is timed in a separate sequential pass" % n_lanes},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "lists_small_kernel<K,PHILOX_TAB,LOSS> (fused sample+order+emit+gather+loss+bwd)",
+                         "traffic": traffic,
+                         "kernel": ("lists_small_kernel<K,PHILOX_TAB,LOSS>" if K <= 16 else
+                                    "lists_large_kernel<LPL,IPL,PHILOX_TAB,LOSS>") +
+                                   " (fused sample+order+emit+gather+loss+bwd)",
                          "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
         }

@@ -64,6 +64,12 @@ CASES = [
     ("purely_k50", "PurelyMaskedRandomSamplingStrategy", 40, 48, 40, 48, 50, 20, 1.0, 21, "perm", True),
     ("thresholded_k33", "ThresholdedMaskedRandomSamplingStrategy", 40, 48, 40, 48, 33, 16, None, 22, "perm", True),
     ("information_k130", "InformationScoreBasedSampling", 40, 48, 40, 48, 130, 6, None, 23, "perm", False),
+    # score-based strategies on down-scaled / holed masks, the shortest list, a larger call
+    ("thresholded_scaled_k4", "ThresholdedMaskedRandomSamplingStrategy", 24, 32, 12, 16, 4, 30, None, 24, "ladder", True),
+    ("information_holes_k8", "InformationScoreBasedSampling", 32, 24, 32, 24, 8, 25, None, 25, "perm", True),
+    ("masked_k2", "MaskedRandomSamplingStrategy", 40, 48, 40, 48, 2, 16, None, 26, "ladder", True),
+    ("information_scaled_k6", "InformationScoreBasedSampling", 24, 32, 8, 8, 6, 20, None, 27, "ladder", False),
+    ("thresholded_k16_r60", "ThresholdedMaskedRandomSamplingStrategy", 48, 64, 48, 64, 16, 60, None, 29, "ladder", True),
 ]
 
 

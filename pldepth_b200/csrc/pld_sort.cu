@@ -18,6 +18,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 elements per CTA; warp w owns elements [256 w, 256 (w + 1))
 constexpr int RS_BINS = 256;
+static_assert(RS_THREADS == RS_BINS, "one thread per digit in the scatter and scan kernels");
 
 struct SegInfo {
   const int* len_dev;                 // per-image live length (nullable)
@@ -106,15 +107,21 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist
 
 // Stable scatter.  Every warp owns 256 consecutive elements of the tile (8 rounds of 32, kept in registers) and
 // ranks them against its own running digit counters: __match_any_sync gives the rank among equal digits of a round,
-// the counter the number of equal digits in the warp's earlier rounds.  Two block barriers per tile: after the
-// counting walk the per-warp counters are turned into global offsets (tile offset of the digit + counts of the
-// lower warps), then every element is written to offset + rank.
+// the counter the number of equal digits in the warp's earlier rounds.  The tile is then put in digit order in shared
+// memory and written out by consecutive threads, so equal digits leave as contiguous runs: scattered 8-byte stores
+// are limited by the SM's request rate (0.66 lane/clk), not by bytes, and one request per run
+// instead of one per element is what this buys.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
                                                                 uint64_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                                                                 SegInfo seg, int pass, int nblk,
                                                                 const int* __restrict__ hist,
                                                                 const int* __restrict__ dig_off) {
-  __shared__ int s_cnt[RS_WARPS][RS_BINS];   // running count while ranking, then the warp's global digit offset
+  __shared__ int s_cnt[RS_WARPS][RS_BINS];   // running count while ranking, then the warp's offset inside its digit run
+  __shared__ int s_start[RS_BINS];           // first position of the digit inside the digit-ordered tile
+  __shared__ int s_gbase[RS_BINS];           // global position of the first element of (this tile, digit)
+  __shared__ int s_wsum[RS_WARPS];
+  __shared__ uint64_t s_key[RS_TILE];
+  __shared__ uint32_t s_val[RS_TILE];
   const int b = blockIdx.y, tile = blockIdx.x;
   if (seg.skip(b, pass)) return;
   const int n = seg.len(b);
@@ -132,11 +139,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __rest
   __syncthreads();
   const int wbase = base + wid * (RS_ITEMS * 32);
   uint64_t k[RS_ITEMS];
+  uint32_t v[RS_ITEMS];
   int rank[RS_ITEMS];
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const int idx = wbase + r * 32 + lane;
     k[r] = (idx < n) ? keys_in[idx] : 0ull;
+    v[r] = (idx < n) ? vals_in[idx] : 0u;
   }
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
@@ -151,25 +160,53 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __rest
     rank[r] = prev + rw;
   }
   __syncthreads();
-  if (threadIdx.x < RS_BINS) {
-    // digit d = threadIdx.x: global position of the first element of (this tile, digit d), then per warp
-    int run = dig_off[b * RS_BINS + threadIdx.x] + hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x];
+  // digit d = threadIdx.x (RS_THREADS == RS_BINS): offsets of the warps inside the digit run, tile count of the digit
+  int cnt = 0;
+  {
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const int c = s_cnt[w][threadIdx.x];
-      s_cnt[w][threadIdx.x] = run;
-      run += c;
+      s_cnt[w][threadIdx.x] = cnt;
+      cnt += c;
+    }
+    s_gbase[threadIdx.x] = dig_off[b * RS_BINS + threadIdx.x] + hist[((size_t)b * nblk + tile) * RS_BINS + threadIdx.x];
+  }
+  // exclusive scan of the 256 digit counts (warp shuffles + warp totals)
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += x;
+  }
+  if (lane == 31) s_wsum[wid] = incl;
+  __syncthreads();
+  {
+    int before = 0;
+    for (int w = 0; w < wid; ++w) before += s_wsum[w];
+    s_start[threadIdx.x] = before + incl - cnt;
+  }
+  __syncthreads();
+  // the tile in digit order (stable: warp order, then round order, then lane order inside a digit)
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    if (wbase + r * 32 + lane < n) {
+      const int d = (int)((k[r] >> shift) & 0xFF);
+      const int lp = s_start[d] + s_cnt[wid][d] + rank[r];
+      s_key[lp] = k[r];
+      s_val[lp] = v[r];
     }
   }
   __syncthreads();
+  const int tile_n = (n - base < RS_TILE) ? (n - base) : RS_TILE;
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const int idx = wbase + r * 32 + lane;
-    if (idx < n) {
-      const int d = (int)((k[r] >> shift) & 0xFF);
-      const int pos = s_cnt[wid][d] + rank[r];
-      keys_out[pos] = k[r];
-      vals_out[pos] = vals_in[idx];
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int lp = i * RS_THREADS + threadIdx.x;
+    if (lp < tile_n) {
+      const uint64_t key = s_key[lp];
+      const int d = (int)((key >> shift) & 0xFF);
+      const int pos = s_gbase[d] + (lp - s_start[d]);
+      keys_out[pos] = key;
+      vals_out[pos] = s_val[lp];
     }
   }
 }

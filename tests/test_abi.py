@@ -77,3 +77,18 @@ def test_header_is_valid_c_and_links_from_plain_c(tmp_path):
                     "-L", libdir, "-l:libpldepth_b200.so", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.split()[0] == "100"
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of the header and its ctypes binding take the same number of arguments (a drifted binding would
+    pass garbage pointers to the kernels)."""
+    from pldepth_b200 import _lib
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(pld_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, args in protos:
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), "%s: header has %d arguments, ctypes binding %d" % (
+            name, n, len(_lib.SIGNATURES[name][1]))

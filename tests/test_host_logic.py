@@ -69,3 +69,19 @@ def test_no_cpu_fallback():
     from pldepth_b200._lib import PLDError
     with pytest.raises(PLDError):
         ops.as_cuda(torch.zeros(3), torch.float32, "x")
+
+
+def test_algorithmic_bytes_match_the_survey_figures():
+    """fused op = 16 B/pixel + 8 B/point (+ loss): 72.1 B/list at config 2, 464 at config 3,
+    92.6 at config 5 -- the numerator of bench.py's roofline."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for (B, H, W, K, R), want in (((32, 448, 448, 5, 100000), 72.1), ((16, 448, 448, 50, 50000), 464.0),
+                                  ((256, 1024, 768, 10, 1000000), 92.6)):
+        L = B * R
+        got = bench.algorithmic_bytes(B, H * W, L, K) / L
+        assert abs(got - want) < 0.06, (got, want)

@@ -588,7 +588,9 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   const size_t off_counts = 0, off_nv = al(sizeof(int) * (size_t)B * nchunks);
   const size_t off_tab = off_nv + al(sizeof(int32_t) * (size_t)B);
   // valid-index mode: holed masks, gradient wanted, rankings not materialised (nothing needs the pixel index)
-  const bool vj_mode = (rankings == nullptr) && (grad != nullptr) && !ctx->deterministic;
+  // -- only while the mask -> image map int(r * H / Hm) is injective (mask not finer than the image): a finer mask sends
+  // several valid indices to one pixel, whose contributions must ACCUMULATE, which the dense-map path does
+  const bool vj_mode = (rankings == nullptr) && (grad != nullptr) && !ctx->deterministic && Hm <= H && Wm <= W;
   const size_t off_vjf = off_tab + al(sizeof(float2) * (size_t)B * tstride);
   const size_t off_gv = off_vjf + (vj_mode ? al(sizeof(int32_t) * (size_t)B * tstride) : 0);
   const size_t scratch_total = off_gv + (vj_mode ? al(sizeof(float) * (size_t)B * tstride) : 0);

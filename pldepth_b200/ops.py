@@ -1,5 +1,8 @@
 """Functional wrappers over the C ABI for tensors that live on a CUDA device.
 
+Every wrapper runs on the calling thread's context (``Context.current``) unless a private one is passed as
+``ctx=`` (the staged helpers a step object with its own context uses).
+
 PyTorch is used only as plumbing: it owns device memory and the current stream.  Any object
 exporting ``__dlpack__`` (e.g. a TensorFlow tensor via ``tf.experimental.dlpack``) is
 accepted and viewed zero-copy.  Every function enqueues on ``torch.cuda.current_stream()``
@@ -40,7 +43,7 @@ def _ctx(t):
     return Context.current(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
-def mask_compact(mask, H, W):
+def mask_compact(mask, H, W, ctx=None):
     """mask f32[B,Hm,Wm] -> (valid_flat i32[B,Hm*Wm], n_valid i32[B]).  sampling.py:124-135.
     A negative n_valid[b] marks the identity table of a fully valid image-resolution mask (row
     not written; M = -n_valid[b]) -- see include/pldepth_b200.h."""
@@ -50,7 +53,7 @@ def mask_compact(mask, H, W):
     if mask.dim() == 4 and mask.shape[-1] == 1:
         mask = mask[..., 0].contiguous()
     B, Hm, Wm = mask.shape
-    ctx = _ctx(mask)
+    ctx = ctx if ctx is not None else _ctx(mask)
     with torch.cuda.device(mask.device):
         valid_flat = torch.empty((B, Hm * Wm), dtype=torch.int32, device=mask.device)
         n_valid = torch.empty((B,), dtype=torch.int32, device=mask.device)
@@ -71,10 +74,10 @@ def _gt2d(gt):
 
 
 def sample_lists_philox(gt, valid_flat, n_valid, K, n, seed, offset=0, image_base=0, want_sel=False,
-                        want_rankings=True):
+                        want_rankings=True, ctx=None):
     gt = _gt2d(gt)
     B, HW = gt.shape
-    ctx = _ctx(gt)
+    ctx = ctx if ctx is not None else _ctx(gt)
     with torch.cuda.device(gt.device):
         rankings = torch.empty((B, n, K, 2), dtype=torch.float32, device=gt.device) if want_rankings else None
         sel = torch.empty((B, n, K), dtype=torch.int32, device=gt.device) if want_sel else None
@@ -130,20 +133,21 @@ def mt19937_generate(state, pos, n):
     return out
 
 
-def gt_minmax(gt):
+def gt_minmax(gt, ctx=None):
     gt = _gt2d(gt)
     B, HW = gt.shape
-    ctx = _ctx(gt)
+    ctx = ctx if ctx is not None else _ctx(gt)
     with torch.cuda.device(gt.device):
         out = torch.empty((B, 2), dtype=torch.float32, device=gt.device)
         check(ctx.lib.pld_gt_minmax(ctx.handle, _p(gt), B, HW, _p(out), _stream(gt.device)))
     return out
 
 
-def score_lists(rankings, strategy, threshold=0.03, equality_penalty=-1000, promotion="nep50", minmax=None):
+def score_lists(rankings, strategy, threshold=0.03, equality_penalty=-1000, promotion="nep50", minmax=None,
+                ctx=None):
     rankings = as_cuda(rankings, torch.float32, "rankings")
     B, n, K, _ = rankings.shape
-    ctx = _ctx(rankings)
+    ctx = ctx if ctx is not None else _ctx(rankings)
     with torch.cuda.device(rankings.device):
         scores = torch.empty((B, n), dtype=torch.float64, device=rankings.device)
         check(ctx.lib.pld_score_lists(ctx.handle, _p(rankings), _p(minmax), B, n, K, _lib.STRATEGY[strategy],
@@ -152,11 +156,11 @@ def score_lists(rankings, strategy, threshold=0.03, equality_penalty=-1000, prom
     return scores
 
 
-def select_top(scores, rankings, R, want_order=False):
+def select_top(scores, rankings, R, want_order=False, ctx=None):
     rankings = as_cuda(rankings, torch.float32, "rankings")
     scores = as_cuda(scores, torch.float64, "scores")
     B, n, K, _ = rankings.shape
-    ctx = _ctx(rankings)
+    ctx = ctx if ctx is not None else _ctx(rankings)
     with torch.cuda.device(rankings.device):
         out = torch.empty((B, R, K, 2), dtype=torch.float32, device=rankings.device)
         order = torch.empty((B, R), dtype=torch.int32, device=rankings.device) if want_order else None
@@ -166,7 +170,7 @@ def select_top(scores, rankings, R, want_order=False):
 
 
 def listmle_fwd_bwd(rankings, pred, B, K, scale, want_grad=True, want_per_list=False, grad_out=None,
-                    accumulate=False):
+                    accumulate=False, ctx=None):
     """rankings f32[B,R,K,2] (any shape reshapable to it), pred f32[B,...].
     Returns (loss f32[1], loss_sum f64[1], grad like pred | None, per_list f32[B*R] | None)."""
     rankings = as_cuda(rankings, torch.float32, "y_true")
@@ -178,7 +182,7 @@ def listmle_fwd_bwd(rankings, pred, B, K, scale, want_grad=True, want_per_list=F
     if pred.numel() % B != 0:
         raise ValueError("y_pred cannot be viewed as [B, -1]")
     HW = pred.numel() // B
-    ctx = _ctx(pred)
+    ctx = ctx if ctx is not None else _ctx(pred)
     dev = pred.device
     with torch.cuda.device(dev):
         loss = torch.empty(1, dtype=torch.float32, device=dev)

@@ -62,12 +62,51 @@ class FusedPLStep(object):
         """gt f32[B,H,W], mask f32[B,Hm,Wm], pred f32[B,H,W(,1)] on one CUDA device.
         Returns dict(loss f32[1], loss_sum f64[1], grad f32[B,H,W,1], rankings f32[B,R,K,2]|None).
         ``loss`` carries the factor 1/(global_batch*R) (global_batch defaults to B)."""
+        gt = ops.as_cuda(gt, torch.float32, "gt")
         if torch.cuda.current_device() != (gt.device.index or 0):
             with torch.cuda.device(gt.device):
                 return self._run(gt, mask, pred, out)
         return self._run(gt, mask, pred, out)
 
+    def _validate(self, gt, mask, pred, out):
+        """The C ABI takes raw pointers: everything that reaches it is float32, dense, on ONE CUDA device and of the
+        shape the call declares.  Dtype / layout mismatches of the inputs are converted (a copy); anything
+        that cannot be fixed by a conversion raises."""
+        gt = ops.as_cuda(gt, torch.float32, "gt")
+        mask = ops.as_cuda(mask, torch.float32, "mask")
+        pred = ops.as_cuda(pred, torch.float32, "pred")
+        if gt.dim() == 4 and gt.shape[-1] == 1:
+            gt = gt[..., 0].contiguous()
+        if mask.dim() == 4 and mask.shape[-1] == 1:
+            mask = mask[..., 0].contiguous()
+        if gt.dim() != 3:
+            raise ValueError("gt must be [B,H,W] (or [B,H,W,1]), got %s" % (tuple(gt.shape),))
+        if mask.dim() != 3 or mask.shape[0] != gt.shape[0]:
+            raise ValueError("mask must be [B,Hm,Wm] with the batch size of gt, got %s" % (tuple(mask.shape),))
+        B, H, W = gt.shape
+        if pred.numel() != B * H * W or pred.shape[0] != B:
+            raise ValueError("pred must hold B*H*W = %d values ([B,H,W] or [B,H,W,1]), got %s" %
+                             (B * H * W, tuple(pred.shape)))
+        if mask.device != gt.device or pred.device != gt.device:
+            raise ValueError("gt, mask and pred must live on the same device")
+        if out is not None:
+            want = {"grad": ((B * H * W,), torch.float32), "loss": ((1,), torch.float32),
+                    "loss_sum": ((1,), torch.float64), "n_valid": ((B,), torch.int32)}
+            if out.get("rankings") is not None:
+                want["rankings"] = ((B * self.R * self.K * 2,), torch.float32)
+            for name, (shape, dtype) in want.items():
+                t = out.get(name)
+                if not isinstance(t, torch.Tensor):
+                    raise ValueError("out[%r] is missing" % name)
+                if t.numel() != shape[0] or t.dtype != dtype or not t.is_contiguous() or t.device != gt.device:
+                    raise ValueError("out[%r] must be a contiguous %s tensor of %d elements on %s" %
+                                     (name, dtype, shape[0], gt.device))
+            if self.emit_rankings and out.get("rankings") is None:
+                raise ValueError("out['rankings'] is required when emit_rankings=True")
+        return gt, mask, pred
+
     def _run(self, gt, mask, pred, out=None):
+        gt, mask, pred = self._validate(gt, mask, pred, out)
         dev = gt.device
         B, H, W = gt.shape[0], gt.shape[1], gt.shape[2]
         Hm, Wm = mask.shape[1], mask.shape[2]
@@ -81,13 +120,14 @@ class FusedPLStep(object):
         if self.strategy != "purely" and self.K > 16:
             # long lists: the scoring pass of the fused kernel is register-resident (K <= 16); above that the
             # staged calls do the same work (candidates are materialised once)
-            vf, nv = ops.mask_compact(mask, H, W)
+            vf, nv = ops.mask_compact(mask, H, W, ctx=ctx)
             cand, _ = ops.sample_lists_philox(gt, vf, nv, self.K, self.n_candidates, self.seed, self.step_index,
-                                              self.image_base)
-            mm = ops.gt_minmax(gt) if self.strategy == "information" else None
-            scores = ops.score_lists(cand, self.strategy, self.threshold, self.equality_penalty, self.promotion, mm)
-            top, _ = ops.select_top(scores, cand, self.R)
-            loss, loss_sum, grad, _ = ops.listmle_fwd_bwd(top, pred, B, self.K, scale, grad_out=buf["grad"])
+                                              self.image_base, ctx=ctx)
+            mm = ops.gt_minmax(gt, ctx=ctx) if self.strategy == "information" else None
+            scores = ops.score_lists(cand, self.strategy, self.threshold, self.equality_penalty, self.promotion, mm,
+                                     ctx=ctx)
+            top, _ = ops.select_top(scores, cand, self.R, ctx=ctx)
+            loss, loss_sum, grad, _ = ops.listmle_fwd_bwd(top, pred, B, self.K, scale, grad_out=buf["grad"], ctx=ctx)
             buf["loss"].copy_(loss)
             buf["loss_sum"].copy_(loss_sum)
             buf["n_valid"].copy_(nv)
@@ -118,6 +158,10 @@ class FusedPLStep(object):
         memory (``pld_ctx_device_offset``), so every ``graph.replay()`` draws fresh lists; new data is fed by
         copying into the same gt / mask / pred tensors.  Returns (graph, output buffers).  While a captured step
         is in use, other Philox calls on this thread's context share (and advance) the same device counter."""
+        for name, t in (("gt", gt), ("mask", mask), ("pred", pred)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("capture(): %s must already be a contiguous float32 CUDA tensor (a converted copy "
+                                 "would be frozen into the graph)" % name)
         dev = gt.device
         ctx = self._ctx if self._ctx is not None else Context.current(dev.index or 0)
         ctx.device_offset(True, self.step_index)

@@ -124,6 +124,25 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
+// Same function with the ten round keys precomputed (kernel-parameter constants: they enter the XORs as constant-bank
+// operands instead of costing two additions per round)
+__device__ __forceinline__ Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    const uint32_t (&rk0)[10], const uint32_t (&rk1)[10]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ rk0[r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+inline void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t (&rk0)[10], uint32_t (&rk1)[10]) {
+  for (int r = 0; r < 10; ++r) { rk0[r] = k0 + (uint32_t)r * 0x9E3779B9u; rk1[r] = k1 + (uint32_t)r * 0xBB67AE85u; }
+}
+
 // Draw stream of one list (see DESIGN.md "Philox stream"):
 //   first attempt of draw k = word (k & 3) of block (k >> 2);
 //   a-th redraw of draw k (Lemire rejection, probability < M / 2^32 each) = word 0 of block

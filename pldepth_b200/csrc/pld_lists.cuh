@@ -37,6 +37,7 @@ struct ListParams {
   int* status;
   int B, HW, valid_stride, n, K;
   uint32_t seed_lo, seed_hi, off_lo, off_hi16;
+  uint32_t rk0[10], rk1[10];             // Philox round keys seed + r * Weyl (filled by the launchers that use them)
   const unsigned long long* offset_dev;  // when set, the Philox offset is read from device memory (graph replay)
   int image_base;
   float scale;

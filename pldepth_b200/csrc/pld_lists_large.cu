@@ -1,103 +1,11 @@
 // Group-per-list kernels for ranking_size 17..512: LPL lanes x IPL register slots per list.
 // Ordering = bitonic network over LPL*IPL slots (shuffles across lanes, register swaps inside
 // a lane); ListMLE = lane-local scans + shuffle scans for the reverse cumsum / prefix sums.
-#include "pld_lists.cuh"
+#include <stdlib.h>
+
+#include "pld_group.cuh"
 
 namespace pld {
-
-// Bitonic network over LPL*IPL slots (slot e = lane*IPL + i), descending, keys as (hi, lo)
-// 32-bit halves.  All keys are distinct (pads: all zero, interchangeable), so "take the partner"
-// is a single predicate and the whole network is branch-free SEL code.
-template <int LPL, int IPL, bool PAYLOAD>
-__device__ __forceinline__ void bitonic_desc(uint32_t (&khi)[IPL], uint32_t (&klo)[IPL], uint32_t (&pay)[IPL], int gl) {
-  constexpr int N = LPL * IPL;
-#pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= IPL) {
-        const int lm = j / IPL;
-        const bool lower = (gl & lm) == 0;
-        const bool up = (gl & (k / IPL)) == 0;  // k/IPL == LPL on the last merge -> always up
-        const bool keep_max = (up == lower);
-#pragma unroll
-        for (int i = 0; i < IPL; ++i) {
-          const uint32_t ohi = __shfl_xor_sync(0xffffffffu, khi[i], lm);
-          const uint32_t olo = __shfl_xor_sync(0xffffffffu, klo[i], lm);
-          const bool gt = (((uint64_t)ohi << 32) | olo) > (((uint64_t)khi[i] << 32) | klo[i]);
-          const bool take = (gt == keep_max);
-          if (PAYLOAD) {
-            const uint32_t op = __shfl_xor_sync(0xffffffffu, pay[i], lm);
-            pay[i] = take ? op : pay[i];
-          }
-          khi[i] = take ? ohi : khi[i];
-          klo[i] = take ? olo : klo[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < IPL; ++i) {
-          if ((i & j) == 0) {
-            const bool up = (((gl * IPL + i) & k) == 0);
-            const uint32_t ah = khi[i], al = klo[i], bh = khi[i | j], bl = klo[i | j];
-            const bool lt = (((uint64_t)ah << 32) | al) < (((uint64_t)bh << 32) | bl);
-            const bool sw = (lt == up);
-            khi[i] = sw ? bh : ah;
-            klo[i] = sw ? bl : al;
-            khi[i | j] = sw ? ah : bh;
-            klo[i | j] = sw ? al : bl;
-            if (PAYLOAD) {
-              const uint32_t pa = pay[i], pb = pay[i | j];
-              pay[i] = sw ? pb : pa;
-              pay[i | j] = sw ? pa : pb;
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-template <int LPL>
-__device__ __forceinline__ float group_max(float v) {
-#pragma unroll
-  for (int o = LPL / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <int LPL>
-__device__ __forceinline__ float group_min(float v) {
-#pragma unroll
-  for (int o = LPL / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <int LPL>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-  for (int o = LPL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// sum of `v` over lanes of the group with a larger / smaller group-lane index
-template <int LPL>
-__device__ __forceinline__ float group_excl_suffix(float v, int gl) {
-  float x = __shfl_down_sync(0xffffffffu, v, 1, LPL);
-  if (gl + 1 >= LPL) x = 0.f;
-#pragma unroll
-  for (int d = 1; d < LPL; d <<= 1) {
-    const float t = __shfl_down_sync(0xffffffffu, x, d, LPL);
-    if (gl + d < LPL) x += t;
-  }
-  return x;
-}
-template <int LPL>
-__device__ __forceinline__ float group_excl_prefix(float v, int gl) {
-  float x = __shfl_up_sync(0xffffffffu, v, 1, LPL);
-  if (gl == 0) x = 0.f;
-#pragma unroll
-  for (int d = 1; d < LPL; d <<= 1) {
-    const float t = __shfl_up_sync(0xffffffffu, x, d, LPL);
-    if (gl >= d) x += t;
-  }
-  return x;
-}
 
 #ifndef PLD_LARGE_MINBLOCKS
 #define PLD_LARGE_MINBLOCKS 4
@@ -318,36 +226,14 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
       }
 
       if (LOSS) {
-        float s[IPL], ex[IPL], S[IPL];
-        float m = -3.402823466e38f;
+        float s[IPL], g[IPL];
 #pragma unroll
         for (int i = 0; i < IPL; ++i) {
           const float sv = have_s ? __uint_as_float(s_tab[i]) : __ldg(pred + p[i]);  // pads: p == 0 is valid
-          s[i] = ((emask >> i) & 1u) ? (((inval >> i) & 1u) ? PLD_LOG_EPS : sv) : -3.402823466e38f;
-          m = fmaxf(m, s[i]);
+          s[i] = ((inval >> i) & 1u) ? PLD_LOG_EPS : sv;
         }
-        m = group_max<LPL>(m);
-        float run = 0.f;
-#pragma unroll
-        for (int i = IPL - 1; i >= 0; --i) {
-          ex[i] = __expf(s[i] - m);  // ex2.approx path; pads: exp(-3.4e38) == 0
-          run += ex[i];
-          S[i] = run;
-        }
-        const float carry = group_excl_suffix<LPL>(run, gl);
-        float nll = 0.f, c = 0.f;
-        float cl[IPL];
-#pragma unroll
-        for (int i = 0; i < IPL; ++i) {
-          const bool on = (emask >> i) & 1u;
-          S[i] += carry;
-          const float term = __logf(S[i]) - (s[i] - m);
-          nll += on ? term : 0.f;
-          c += on ? __fdividef(1.0f, S[i]) : 0.f;
-          cl[i] = c;
-        }
-        const float cpre = group_excl_prefix<LPL>(c, gl);
-        nll = group_sum<LPL>(nll);
+        const int nreal = min(max(K - gl * IPL, 0), IPL);
+        const float nll = group_listmle<LPL, IPL>(s, nreal, gl, g);
         if (active) {
           if (gl == 0) {
             local += nll;
@@ -356,7 +242,7 @@ __global__ void __launch_bounds__(256, PLD_LARGE_MINBLOCKS) lists_large_kernel(c
           if (P.grad != nullptr) {
 #pragma unroll
             for (int i = 0; i < IPL; ++i)
-              if (((emask & ~inval) >> i) & 1u) grad_add(P, grad_dst, map_off, p[i], ex[i] * (cl[i] + cpre) - 1.0f);
+              if (((emask & ~inval) >> i) & 1u) grad_add(P, grad_dst, map_off, p[i], g[i]);
           }
         }
       }
@@ -386,8 +272,13 @@ static int launch_large_cfg(const ListParams& P, int src, bool loss, dim3 grid, 
   return PLD_OK;
 }
 
+int launch_lists_tab(const ListParams& P, bool loss, int num_sms, cudaStream_t st);   // pld_lists_tab.cu
+
 int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cudaStream_t st) {
   const int K = P.K;
+  // the one-call steps run the software-pipelined kernel (PLD_LARGE_LEGACY=1 keeps the round-1 kernel for A/B runs)
+  static const bool legacy = getenv("PLD_LARGE_LEGACY") != nullptr && getenv("PLD_LARGE_LEGACY")[0] == '1';
+  if (src == SRC_PHILOX_TAB && !legacy) return launch_lists_tab(P, loss, num_sms, st);
   int lpl;
   if (K <= 32) lpl = 4;
   else if (K <= 64) lpl = 8;

@@ -1,0 +1,379 @@
+// Software-pipelined group-per-list kernel of the one-call steps for ranking_size 17..512 (BASELINE config 3: K = 50):
+// Philox draws -> one 8-byte lookup-table gather per draw -> per-list order by gt depth -> emit rankings ->
+// ListMLE forward / backward -> gradient reductions.   Same results as lists_large_kernel<.., SRC_PHILOX_TAB, ..>
+// (pld_lists_large.cu), which it replaces on that path; organised around what round 1's profile showed
+// (profiles/r01_c3_final_summary.txt: ALU pipe 68 %, issue 59 %, L1TEX 74 % -- nothing saturated, nothing overlapped):
+//
+//  * the draws and table gathers of list group i+1 are issued BEFORE group i is ordered, so the L1TEX queue is never
+//    empty while a warp runs its ordering network; they land in registers and are parked in shared memory after
+//    group i is finished (cp.async straight into shared memory was measured and rejected: a scattered LDGSTS spends one
+//    shared-memory wavefront per LANE on its write-back, 48 M wavefronts per config-3 launch, profiles/r02_c3_v1);
+//  * the ordering network runs on ONE 32-bit key per entry -- depth prefix | draw slot -- so a compare-exchange is a
+//    min + a max (2 ALU-pipe instructions) instead of a 64-bit compare + four selects; payloads (depth, prediction,
+//    pixel) never travel through the network: they stay parked under their draw slot and are fetched once, by the
+//    slot id that survives in the key's low bits;
+//  * the truncated depth prefix is verified after the fetch (adjacent full depths must be non-increasing); a
+//    group that fails -- two depths of one list equal in their top 32 - log2(slots) bits but not equal -- is re-ordered
+//    by the exact 64-bit network.  Exact ties keep the rule "later draw first" in both networks.
+//
+// Reference semantics: sample_single_masked_ranking (pldepth/data/sampling.py:110-122), prepare_fully_fledged_loss_input
+// (pldepth/data/depth_utils.py:39-61), TF-Ranking ListMLE behind nll_loss.py:43-62.
+#include <type_traits>
+
+#include "pld_group.cuh"
+
+namespace pld {
+
+template <int N> struct ILog2 { static constexpr int v = 1 + ILog2<N / 2>::v; };
+template <> struct ILog2<1> { static constexpr int v = 0; };
+
+// min or max by a per-lane predicate in two issue slots (max; @!keep_max min) -- the select form costs three
+__device__ __forceinline__ uint32_t minmax_pred(uint32_t a, uint32_t o, bool keep_max) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmax.u32 %0, %1, %2;\n\t@!p min.u32 %0, %1, %2;\n\t}"
+      : "=r"(r) : "r"(a), "r"(o), "r"((uint32_t)keep_max));
+  return r;
+}
+
+// Bitonic network, descending, on single 32-bit keys (slot e = lane*IPL + i).  Blocks that the classic network sorts
+// ASCENDING hold their keys complemented instead (x -> ~x reverses the order), so every compare-exchange inside a
+// lane is the same static max / min pair; a lane complements its keys only where its block direction changes between
+// merge levels (IPL LOP3 per level >= IPL).  Across lanes the lower lane keeps the maximum, the upper the minimum.
+template <int LPL, int IPL>
+__device__ __forceinline__ void bitonic_desc32(uint32_t (&key)[IPL], int gl) {
+  constexpr int N = LPL * IPL;
+  uint32_t flipped = 0u;   // all-ones while this lane's keys are stored complemented
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+    if (k >= IPL) {
+      // direction of this lane's block at level k depends on the lane only
+      const uint32_t want = (k < N && ((gl * IPL) & k) != 0) ? 0xFFFFFFFFu : 0u;
+      const uint32_t d = flipped ^ want;
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) key[i] ^= d;
+      flipped = want;
+    }
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= IPL) {
+        const int lm = j / IPL;
+        const bool lower = (gl & lm) == 0;
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, key[i], lm);
+          key[i] = minmax_pred(key[i], o, lower);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          if ((i & j) == 0) {
+            const bool up = (k >= IPL) || ((i & k) == 0);   // static
+            const uint32_t a = key[i], c = key[i | j];
+            key[i] = up ? max(a, c) : min(a, c);
+            key[i | j] = up ? min(a, c) : max(a, c);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Exact fallback: full 64-bit keys (ordered depth, draw slot) rebuilt from the parked entries; returns the draw slot of
+// every sorted position.
+template <int LPL, int IPL>
+__device__ __noinline__ void exact_order(const float2* own, bool gs_layout, uint32_t emask, int gl, uint32_t (&eslot)[IPL]) {
+  uint32_t khi[IPL], klo[IPL], nopay[IPL];
+#pragma unroll
+  for (int i = 0; i < IPL; ++i) {
+    const bool on = (emask >> i) & 1u;
+    const float2 t = on ? own[i] : make_float2(0.f, 0.f);
+    khi[i] = on ? float_to_ordered(gs_layout ? t.x : t.y) : 0u;
+    klo[i] = on ? ((uint32_t)(gl * IPL + i) << 23) : 0u;
+  }
+  bitonic_desc<LPL, IPL, false>(khi, klo, nopay, gl);
+#pragma unroll
+  for (int i = 0; i < IPL; ++i) eslot[i] = klo[i] >> 23;
+}
+
+#ifndef PLD_TAB_MINBLOCKS
+#define PLD_TAB_MINBLOCKS 3
+#endif
+
+template <int LPL, int IPL, int THREADS, bool LOSS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS : 4) lists_tab_kernel(const ListParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // Parking buffers.  A lane owns ROW = IPL + 1 consecutive entries (the odd stride keeps its own 8-byte accesses at the
+  // two-wavefront minimum); draw slot e of a list group sits at  group_base + e + (e >> log2 IPL).  s_ent: one stage (a
+  // warp refills its own rows after it has fetched everything from them); s_aux (selection index): two stages, because
+  // it is written when the draws are made, one group ahead.
+  constexpr int ROW = IPL + 1;
+  constexpr int STAGE = ROW * THREADS;
+  float2* const s_ent = reinterpret_cast<float2*>(smem_raw);
+  uint32_t* const s_aux = reinterpret_cast<uint32_t*>(smem_raw + (size_t)STAGE * sizeof(float2));
+  constexpr int GPW = 32 / LPL;         // list groups per warp
+  constexpr int GPB = THREADS / LPL;    // list groups per CTA
+  constexpr int SLOT_BITS = ILog2<LPL * IPL>::v;
+  constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1u;
+  constexpr int LOG_IPL = ILog2<IPL>::v;
+  const int K = P.K;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int gl = lane & (LPL - 1);
+  const int own = tid * ROW;                       // this lane's row
+  const int grp = (tid & ~(LPL - 1)) * ROW;        // first row of its list group
+  // real entries of this lane: slots / sorted positions gl*IPL + i with i < nreal
+  const int nreal = min(max(K - gl * IPL, 0), IPL);
+  const uint32_t emask = (1u << nreal) - 1u;
+  const size_t map_off = (size_t)b * (size_t)P.HW;
+  const float* __restrict__ pred = P.pred + map_off;
+  float local = 0.f;
+  int bad = 0;
+  uint32_t off_lo, off_hi16;
+  launch_offset(P, off_lo, off_hi16);
+
+  uint32_t M = 0, thresh = 0;
+  bool identity = false;
+  {
+    const int mraw = P.n_valid[b];
+    const int m = mraw < 0 ? -mraw : mraw;
+    if (m == 0) bad |= PLD_ST_EMPTY_MASK;
+    else { M = (uint32_t)m; thresh = (0u - M) % M; }
+    identity = mraw < 0;
+  }
+  const bool vj = !identity && P.grad_valid != nullptr;
+  const bool gs_layout = identity || vj;      // table entry = (gt, pred); else (bits of the pixel index, gt)
+  float* grad_dst = P.grad == nullptr ? nullptr : (vj ? P.grad_valid + (size_t)b * P.table_stride : P.grad + map_off);
+  const float2* __restrict__ tab = P.table + (size_t)b * P.table_stride;
+  const uint32_t* __restrict__ lmap = P.list_map != nullptr ? P.list_map + (size_t)b * P.map_stride : nullptr;
+  const uint32_t image = (uint32_t)(P.image_base + b);
+
+  // ---- stage A: draws of one list group; table gathers issued into registers, selections parked in aux[stage] ---------
+  auto issue = [&](int l0, int stage, float2 (&nt)[IPL]) {
+    const int lraw = l0 + lane / LPL;
+    const int l = lraw < P.n ? lraw : P.n - 1;
+    const uint32_t lid = lmap != nullptr ? __ldg(lmap + l) : (uint32_t)l;
+    uint32_t sel[IPL];
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) sel[i] = 0u;
+    bool rej = false;
+#pragma unroll
+    for (int q = 0; q < IPL / 4; ++q) {
+      const int e0 = gl * IPL + q * 4;
+      if (e0 < K) {
+        const Philox4 r = philox4x32_10_rk(lid, image, (uint32_t)(e0 >> 2) | off_hi16, off_lo, P.rk0, P.rk1);
+        sel[q * 4 + 0] = lemire_try(r.x, M, thresh, rej);
+        sel[q * 4 + 1] = lemire_try(r.y, M, thresh, rej);
+        sel[q * 4 + 2] = lemire_try(r.z, M, thresh, rej);
+        sel[q * 4 + 3] = lemire_try(r.w, M, thresh, rej);
+      }
+    }
+    if (rej) {  // rare (P < K * M / 2^32): redo this lane's draws with the redraw stream
+      const DrawStream ds{lid, image, off_lo, off_hi16, P.seed_lo, P.seed_hi};
+#pragma unroll
+      for (int q = 0; q < IPL / 4; ++q) {
+        const int e0 = gl * IPL + q * 4;
+        if (e0 < K) {
+          const Philox4 r = ds.block((uint32_t)(e0 >> 2));
+          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sel[q * 4 + j] = lemire_bounded(w[j], M, thresh, ds, (uint32_t)(e0 + j));
+        }
+      }
+    }
+    // pad slots gather entry 0 (one shared sector) so that the loads need no predicate
+    uint32_t* aux = s_aux + stage * STAGE + own;
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) {
+      nt[i] = __ldg(tab + sel[i]);
+      aux[i] = sel[i];
+    }
+    if (P.sel_out != nullptr && lraw < P.n) {
+      int32_t* so = P.sel_out + ((size_t)b * (size_t)P.n + (size_t)l) * K;
+#pragma unroll
+      for (int i = 0; i < IPL; ++i)
+        if (i < nreal) so[gl * IPL + i] = (int32_t)sel[i];
+    }
+  };
+
+  // ---- stage B: order, emit, loss, gradient of the group parked in s_ent / aux[stage] -------------------------------
+  auto process = [&](int l0, int stage, auto gs_tag) {
+    constexpr bool GS = decltype(gs_tag)::value;
+    const int lraw = l0 + lane / LPL;
+    const bool active = lraw < P.n;
+    const int l = active ? lraw : (P.n - 1);
+    const size_t list_id = (size_t)b * (size_t)P.n + (size_t)l;
+    uint32_t* aux = s_aux + stage * STAGE;
+
+    // own draw slots -> 32-bit keys: ordered depth with its low SLOT_BITS replaced by the draw slot; pads = bare slot
+    uint32_t key[IPL];
+    float spre[GS ? 1 : IPL];
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) {
+      const float2 t = s_ent[own + i];
+      const uint32_t slot = (uint32_t)(gl * IPL + i);
+      key[i] = (i < nreal) ? ((float_to_ordered(GS ? t.x : t.y) & ~SLOT_MASK) | slot) : slot;
+      // pixel layout (holed mask, rankings emitted): the prediction needs its own gather, issued here so that its
+      // latency hides behind the ordering network (pads hold entry 0 = a valid pixel)
+      if (!GS && LOSS) spre[i] = __ldg(pred + __float_as_int(t.x));
+    }
+    bitonic_desc32<LPL, IPL>(key, gl);
+    if (!GS && LOSS) {
+      // park the predictions under their draw slots (the selection index is not needed in this layout)
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) aux[own + i] = __float_as_uint(spre[i]);
+    }
+    __syncwarp();
+
+    // fetch the parked payloads by surviving slot id
+    float2 e2[IPL];
+    uint32_t ax[IPL];
+    uint32_t eslot[IPL];
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) eslot[i] = key[i] & SLOT_MASK;
+    auto unpark = [&]() {
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) {
+        const int src = grp + (int)(eslot[i] + (eslot[i] >> LOG_IPL));
+        e2[i] = s_ent[src];
+        ax[i] = aux[src];
+      }
+    };
+    unpark();
+    // verify the truncated order on the full depths
+    {
+      bool viol = false;
+      uint32_t og[IPL];
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) og[i] = float_to_ordered(GS ? e2[i].x : e2[i].y);
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) {
+        if (i < nreal && eslot[i] >= (uint32_t)K) viol = true;                  // a pad sorted in front of a real entry
+        if (i + 1 < IPL && i + 1 < nreal && og[i] < og[i + 1]) viol = true;
+      }
+      const uint32_t nxt = __shfl_down_sync(0xffffffffu, og[0], 1, LPL);
+      if (gl + 1 < LPL && (gl + 1) * IPL < K && og[IPL - 1] < nxt) viol = true;
+      if (__any_sync(0xffffffffu, viol)) {
+        uint32_t ex_slot[IPL];     // separate array: its address escapes into the call, eslot must stay in registers
+        exact_order<LPL, IPL>(s_ent + own, GS, emask, gl, ex_slot);
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) eslot[i] = ex_slot[i];
+        unpark();
+      }
+    }
+
+    int p[IPL];
+    float lab[IPL], sv[IPL];
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) {
+      if (GS) { lab[i] = e2[i].x; sv[i] = e2[i].y; p[i] = (int)ax[i]; }
+      else { lab[i] = e2[i].y; sv[i] = __uint_as_float(ax[i]); p[i] = __float_as_int(e2[i].x); }
+    }
+    if (P.rank_out != nullptr && active) {
+      float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K + gl * IPL;
+      if ((K & 1) == 0) {  // 16-byte stores: list rows are 16-byte aligned when K is even
+#pragma unroll
+        for (int i = 0; i < IPL; i += 2)
+          if (i < nreal)
+            *reinterpret_cast<float4*>(ro + i) = make_float4((float)p[i], lab[i], (float)p[i + 1], lab[i + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < IPL; ++i)
+          if (i < nreal) ro[i] = make_float2((float)p[i], lab[i]);
+      }
+    }
+
+    if (LOSS) {
+      float g[IPL];
+      const float nll = group_listmle<LPL, IPL>(sv, nreal, gl, g);
+      if (active && gl == 0) {
+        local += nll;
+        if (P.per_list != nullptr) P.per_list[list_id] = nll;
+      }
+      if (P.grad != nullptr) {
+        const int lim = active ? nreal : 0;
+        if (P.acc != nullptr) {   // deterministic mode: 64-bit fixed-point atomics
+#pragma unroll
+          for (int i = 0; i < IPL; ++i)
+            if (i < lim) grad_add(P, grad_dst, map_off, p[i], g[i]);
+        } else {
+          const float sc = P.scale;
+#pragma unroll
+          for (int i = 0; i < IPL; ++i)
+            if (i < lim) red_add_f32(grad_dst + p[i], g[i] * sc);
+        }
+      }
+    }
+    __syncwarp();   // every lane is done with the parked group before it is overwritten
+  };
+
+  if (M != 0) {
+    const int stride = gridDim.x * GPB;
+    int l0 = blockIdx.x * GPB + (tid >> 5) * GPW;
+    int stage = 0;
+    float2 nt[IPL];
+    if (l0 < P.n) {
+      issue(l0, 0, nt);
+#pragma unroll
+      for (int i = 0; i < IPL; ++i) s_ent[own + i] = nt[i];
+      __syncwarp();
+    }
+    for (; l0 < P.n; l0 += stride) {
+      const bool more = l0 + stride < P.n;     // uniform per warp
+      if (more) issue(l0 + stride, stage ^ 1, nt);
+      if (gs_layout) process(l0, stage, std::true_type{});
+      else process(l0, stage, std::false_type{});
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) s_ent[own + i] = nt[i];
+        __syncwarp();
+      }
+      stage ^= 1;
+    }
+  }
+  if (bad) atomicOr(P.status, bad);
+  if (LOSS) block_loss_epilogue(local, P.partials, P.ticket, P.scale, P.loss, P.loss_sum);
+}
+
+template <int LPL, int IPL, int THREADS>
+static int launch_tab_cfg(const ListParams& P, bool loss, int num_sms, cudaStream_t st) {
+  constexpr size_t SMEM = (size_t)(IPL + 1) * THREADS * (sizeof(float2) + 2 * sizeof(uint32_t));
+  static bool configured[2] = {false, false};
+  if (!configured[loss ? 1 : 0]) {
+    cudaError_t e = loss ? cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)
+                         : cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(lists_tab_kernel) failed: %s", cudaGetErrorString(e));
+      return PLD_ECUDA;
+    }
+    configured[loss ? 1 : 0] = true;
+  }
+  constexpr int GPB = THREADS / LPL;
+  const int per_image_cap = lists_per_image_cap(num_sms, P.B);
+  int gx = (P.n + GPB - 1) / GPB;
+  if (gx > per_image_cap) gx = per_image_cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)P.B);
+  ListParams Q = P;
+  philox_round_keys(P.seed_lo, P.seed_hi, Q.rk0, Q.rk1);
+  if (loss) lists_tab_kernel<LPL, IPL, THREADS, true><<<grid, THREADS, SMEM, st>>>(Q);
+  else lists_tab_kernel<LPL, IPL, THREADS, false><<<grid, THREADS, SMEM, st>>>(Q);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+// SRC_PHILOX_TAB for 17 <= K <= 512
+int launch_lists_tab(const ListParams& P, bool loss, int num_sms, cudaStream_t st) {
+  const int K = P.K;
+  if (K <= 32) return launch_tab_cfg<4, 8, 256>(P, loss, num_sms, st);
+  if (K <= 64) return launch_tab_cfg<8, 8, 256>(P, loss, num_sms, st);
+  if (K <= 128) return launch_tab_cfg<16, 8, 256>(P, loss, num_sms, st);
+  if (K <= 256) return launch_tab_cfg<32, 8, 256>(P, loss, num_sms, st);
+  if (K <= 512) return launch_tab_cfg<32, 16, 128>(P, loss, num_sms, st);
+  set_error("lists_tab: K=%d out of range", K);
+  return PLD_EINVAL;
+}
+
+}  // namespace pld

@@ -27,6 +27,15 @@ namespace pld {
 template <int N> struct ILog2 { static constexpr int v = 1 + ILog2<N / 2>::v; };
 template <> struct ILog2<1> { static constexpr int v = 0; };
 
+// 8-byte read-only load under a predicate, without a branch; (0, 0) when off
+__device__ __forceinline__ float2 ldg_f2_if(const float2* ptr, bool on) {
+  float2 v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+               "@p ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+               : "=f"(v.x), "=f"(v.y) : "l"(ptr), "r"((uint32_t)on));
+  return v;
+}
+
 // min or max by a per-lane predicate in two issue slots (max; @!keep_max min) -- the select form costs three
 __device__ __forceinline__ uint32_t minmax_pred(uint32_t a, uint32_t o, bool keep_max) {
   uint32_t r;
@@ -181,11 +190,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS 
         }
       }
     }
-    // pad slots gather entry 0 (one shared sector) so that the loads need no predicate
+    // pad slots gather nothing (predicated load: an extra sector per load instruction otherwise) and park (0, 0)
     uint32_t* aux = s_aux + stage * STAGE + own;
 #pragma unroll
     for (int i = 0; i < IPL; ++i) {
-      nt[i] = __ldg(tab + sel[i]);
+      nt[i] = ldg_f2_if(tab + sel[i], i < nreal);
       aux[i] = sel[i];
     }
     if (P.sel_out != nullptr && lraw < P.n) {
@@ -234,7 +243,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS 
     auto unpark = [&]() {
 #pragma unroll
       for (int i = 0; i < IPL; ++i) {
-        const int src = grp + (int)(eslot[i] + (eslot[i] >> LOG_IPL));
+        // pad positions re-read this lane's own row (no new bank, nothing used from it)
+        const int src = (i < nreal) ? grp + (int)(eslot[i] + (eslot[i] >> LOG_IPL)) : own + i;
         e2[i] = s_ent[src];
         ax[i] = aux[src];
       }

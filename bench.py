@@ -49,7 +49,16 @@ def parse_args():
     ap.add_argument("--no-emit", action="store_true", help="do not materialise the rankings (what a fused training "
                                                            "step needs; the default emits them like the reference)")
     ap.add_argument("--hole", type=float, default=0.0, help="fraction of each mask zeroed (default: all-ones mask)")
-    return ap.parse_args()
+    ap.add_argument("--strategy", default="purely", choices=["purely", "masked", "thresholded", "information"],
+                    help="sampling strategy (default: the core sampler, exactly R lists per image)")
+    ap.add_argument("--secondary", dest="secondary", action="store_true", default=None,
+                    help="also measure the secondary workloads (default: on for the default C2 headline at N=1)")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    a = ap.parse_args()
+    if a.secondary is None:
+        a.secondary = (a.workload == "C2" and a.hole == 0.0 and a.strategy == "purely" and not a.no_emit and
+                       a.gpus == 1 and a.impl == "b200")
+    return a
 
 
 def workload_shape(name):
@@ -189,7 +198,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (args.workload, json.dumps(shape)), "sample": sample},
+            "config": {"workload": workload_string(args.workload, shape, args.hole, not args.no_emit, args.strategy),
+                       "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -199,12 +209,250 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
+SM_COUNT = 148
+# micro-benchmark floor of the unit that binds the list kernels (profiles/r01_microbench.jsonl): per SM and clock one
+# divergent 8-byte table gather, 0.66 scattered float reductions, one store sector
+FLOOR_GATHER_CLK, FLOOR_RED_CLK, FLOOR_STORE_SECTOR_CLK = 1.0, 1.0 / 0.66, 1.0
+
+
+def workload_string(name, shape, hole, emit, strategy):
+    """One description of the measured configuration, identical in both arms."""
+    return "%s per GPU: B=%d images %dx%d, ranking_size K=%d, R=%d lists/image, %s mask, %s, rankings %s" % (
+        name, shape["B"], shape["H"], shape["W"], shape["K"], shape["R"],
+        "all-ones" if hole == 0 else "%.0f%%-hole" % (100 * hole),
+        "core sampler (factor 1.0)" if strategy == "purely" else "%s strategy (R best of its candidates)" % strategy,
+        "emitted" if emit else "not materialised")
+
+
+def synthetic_batch(name, shape, hole, rank):
+    import numpy as np
+    from pldepth_b200 import synth
+    B, H, W = shape["B"], shape["H"], shape["W"]
+    cfg_id = {"C1": 1, "C2": 2, "C3": 3, "C5s": 5, "C5": 5}[name]
+    # a few distinct rank-transformed fields, rolled to make B distinct images
+    base_maps = [synth.depth_map(H, W, 1000 * cfg_id + 17 * rank + i) for i in range(min(B, 4))]
+    gt_h = np.stack([np.roll(base_maps[b % len(base_maps)], 31 * b, axis=1) for b in range(B)])
+    mask_h = np.stack([synth.valid_mask(H, W, 3000 * cfg_id + b, hole) for b in range(B)])
+    pred_h = np.random.RandomState(2000 * cfg_id + rank).standard_normal((B, H, W, 1)).astype(np.float32)
+    return cfg_id, gt_h, mask_h, pred_h
+
+
+class Measurement(object):
+    """Device-resident measurement of one workload: rotating buffer sets, optional lanes, kernel-alone timing."""
+
+    def __init__(self, name, shape, hole, emit, strategy, n_sets, want_lanes, world, rank, local_rank, graph=False):
+        import numpy as np
+        import torch
+        from pldepth_b200._lib import Context
+        from pldepth_b200.dist import LossWindow
+        from pldepth_b200.step import FusedPLStep
+        self.torch, self.np = torch, np
+        self.name, self.shape, self.hole, self.emit, self.strategy = name, shape, hole, emit, strategy
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+        dev = self.dev = torch.device("cuda", local_rank)
+        B, H, W, K, R = shape["B"], shape["H"], shape["W"], shape["K"], shape["R"]
+        self.L = B * R
+        self.cfg_id, self.gt_h, self.mask_h, self.pred_h = synthetic_batch(name, shape, hole, rank)
+        self.n_sets = n_sets = max(1, n_sets)
+        self.sets = []
+        for s in range(n_sets):
+            self.sets.append(dict(gt=torch.from_numpy(np.roll(self.gt_h, s, axis=0)).to(dev),
+                                  mask=torch.from_numpy(self.mask_h).to(dev),
+                                  pred=torch.from_numpy(np.roll(self.pred_h, s, axis=0)).to(dev),
+                                  out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev, emit_rankings=emit)))
+        n_lanes = 1 if graph else max(1, min(want_lanes, n_sets))
+        while n_sets % n_lanes:      # a buffer set must always be used by the same lane (stream order protects it)
+            n_lanes -= 1
+        self.n_lanes = n_lanes
+        mk = lambda l: FusedPLStep(K, R, seed=self.cfg_id, global_batch=B * world, image_base=rank * B,
+                                   emit_rankings=emit, strategy=strategy,
+                                   context=None if l == 0 else Context(local_rank), first_step=l << 24)
+        self.lane_steps = [mk(l) for l in range(n_lanes)]
+        self.lane_streams = [torch.cuda.current_stream(dev)] + [torch.cuda.Stream(dev) for _ in range(1, n_lanes)]
+        # The path's only exchange -- the SUM of one float64 per step -- is taken off the step: every step writes its
+        # local loss sum into a slot of its lane's window (the fused step takes the pointer), and a window is
+        # all-reduced once per WINDOW steps.  Two windows per lane alternate, so a step never waits for a reduction.
+        self.window_steps = 16
+        self.windows = [[LossWindow(self.window_steps, dev), LossWindow(self.window_steps, dev)] for _ in range(n_lanes)]
+        self.win_work = [[None, None] for _ in range(n_lanes)]
+        self.lane_count = [0] * n_lanes
+        self.reductions = 0
+        self.last_losses = None
+
+    def _close_window(self, lane, which):
+        import torch.distributed as dist
+        w = self.windows[lane][which]
+        if w.filled == 0:
+            return
+        self.win_work[lane][which] = w.reduce(async_op=True) if self.world > 1 else w.reduce()
+        self.reductions += 1 if self.world > 1 else 0
+        self.last_losses = (lane, which)
+
+    def one_step(self, i, lanes=None):
+        torch = self.torch
+        lanes = self.n_lanes if lanes is None else lanes
+        s = self.sets[i % self.n_sets]
+        lane = i % lanes
+        with torch.cuda.stream(self.lane_streams[lane]):
+            c = self.lane_count[lane]
+            which = (c // self.window_steps) & 1
+            w = self.windows[lane][which]
+            if c % self.window_steps == 0 and self.win_work[lane][which] is not None:
+                self.win_work[lane][which].wait()        # stream-level wait for this window's previous reduction
+                self.win_work[lane][which] = None
+            s["out"]["loss_sum"] = w.slot(c)
+            out = self.lane_steps[lane].run(s["gt"], s["mask"], s["pred"], out=s["out"])
+            self.lane_count[lane] = c + 1
+            if w.mark():
+                self._close_window(lane, which)
+        return out
+
+    def drain(self):
+        """Reduce every partially filled window and wait (stream-level) for all outstanding reductions."""
+        torch = self.torch
+        for lane in range(self.n_lanes):
+            with torch.cuda.stream(self.lane_streams[lane]):
+                for which in (0, 1):
+                    self._close_window(lane, which)
+                    if self.win_work[lane][which] is not None:
+                        self.win_work[lane][which].wait()
+                        self.win_work[lane][which] = None
+                # restart window accounting on a boundary
+                self.lane_count[lane] = ((self.lane_count[lane] + self.window_steps - 1) // self.window_steps) * self.window_steps
+
+    def fork_lanes(self, ev):
+        for st in self.lane_streams[1:]:
+            st.wait_event(ev)
+
+    def join_lanes(self):
+        cur = self.torch.cuda.current_stream(self.dev)
+        for st in self.lane_streams[1:]:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.drain()
+        self.join_lanes()
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def check(self):
+        for ls in self.lane_steps:
+            ls.check(self.dev)
+
+    def kernel_alone(self, n_k):
+        """Mean duration of the dominant (list) kernel over a strictly sequential pass: the library records CUDA
+        events around that launch on its stream (pld_ctx_kernel_timing).  Also returns the sequential step time."""
+        from pldepth_b200._lib import Context
+        torch = self.torch
+        ctx = Context.current(self.local_rank)
+        ctx.kernel_timing(n_k)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(n_k):
+            self.one_step(i, lanes=1)
+        b_.record()
+        self.drain()
+        torch.cuda.synchronize()
+        kms = ctx.kernel_times(n_k)
+        ctx.kernel_timing(0)
+        return sum(kms) / max(len(kms), 1), a.elapsed_time(b_) / n_k
+
+    def timed(self, steps, graphs=None):
+        import torch.distributed as dist
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        self.fork_lanes(e0)
+        for i in range(steps):
+            if graphs is not None:
+                graphs[i % self.n_sets].replay()
+            else:
+                self.one_step(i)
+        self.drain()
+        self.join_lanes()
+        e1.record()
+        self.barrier()
+        ms_total = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms_total], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        return ms_total
+
+    def roofline(self, k_ms, ms_per_step, seq_ms_per_step, peak, peak_src, sm_mhz):
+        B, H, W, K, R = (self.shape[k] for k in "BHWKR")
+        abytes = algorithmic_bytes(B, H * W, self.L, K) if self.emit else B * H * W * 16 + 4
+        achieved = abytes / (k_ms * 1e-3) / 1e9
+        clk = (sm_mhz or 1965.0) * 1e6
+        cyc = k_ms * 1e-3 * clk * SM_COUNT / self.L
+        floor = K * (FLOOR_GATHER_CLK + FLOOR_RED_CLK) + (K * 8.0 / 32.0) * FLOOR_STORE_SECTOR_CLK * (1 if self.emit else 0)
+        if self.hole > 0 and self.emit and self.strategy == "purely":
+            floor += K * FLOOR_GATHER_CLK       # holed + emitted: the prediction needs its own gather
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "step_frac": abytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "step_frac_sequential": abytes / (seq_ms_per_step * 1e-3) / 1e9 / peak,
+                "kernel": ("lists_small_kernel<K,PHILOX_TAB,LOSS>" if K <= 16 else
+                           "lists_tab_kernel<LPL,IPL,THREADS,LOSS>") + " (fused sample+order+emit+gather+loss+bwd)",
+                "kernel_ms": k_ms, "sequential_ms_per_step": seq_ms_per_step, "algorithmic_bytes": abytes,
+                "peak_source": peak_src,
+                "binding_unit": {"unit": "L1TEX sector operations (divergent gathers, reductions, store sectors)",
+                                 "sm_cycles_per_list": cyc, "microbench_floor_cycles_per_list": floor,
+                                 "frac_of_floor": floor / cyc,
+                                 "source": "profiles/r01_microbench.jsonl: 1.0 gather, 0.66 reduction, 1 store sector "
+                                           "per SM and clock; DESIGN.md section 4"}}
+
+    def free(self):
+        self.sets = None
+        self.lane_steps = None
+        self.torch.cuda.empty_cache()
+
+
+def secondary_rows(world, rank, local_rank, peak, peak_src, sm_mhz):
+    """The workloads the reference really runs, measured in the same process after the headline (sequential steps,
+    few iterations): holed masks, long lists, the config-5 share, the default (InformationScore) strategy."""
+    rows = []
+    plan = [("C2", 0.1, True, "purely"), ("C2", 0.1, False, "purely"), ("C2", 0.0, False, "purely"),
+            ("C3", 0.0, True, "purely"), ("C3", 0.0, False, "purely"), ("C5", 0.0, True, "purely"),
+            ("C2", 0.0, True, "information"), ("C2", 0.0, False, "information"),
+            ("C2", 0.0, True, "thresholded"), ("C2", 0.0, False, "thresholded")]
+    for name, hole, emit, strategy in plan:
+        shape = workload_shape(name)
+        try:
+            m = Measurement(name, shape, hole, emit, strategy, 2, 1, world, rank, local_rank)
+            for i in range(3):
+                m.one_step(i)
+            m.barrier()
+            m.check()
+            k_ms, seq_ms = m.kernel_alone(8)
+            ms = m.timed(8) / 8
+            r = m.roofline(k_ms, ms, seq_ms, peak, peak_src, sm_mhz)
+            rows.append({"workload": workload_string(name, shape, hole, emit, strategy), "lists_per_step": m.L * world,
+                         "value": m.L * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": k_ms,
+                         "frac": r["frac"], "step_frac": r["step_frac"],
+                         "sm_cycles_per_list": r["binding_unit"]["sm_cycles_per_list"],
+                         "floor_cycles_per_list": r["binding_unit"]["microbench_floor_cycles_per_list"],
+                         "note": "frac = algorithmic bytes / LAST list kernel of the step; scored strategies run two list "
+                                 "passes plus selection, see step_frac" if strategy != "purely" else
+                                 "frac = algorithmic bytes / list-kernel time"})
+            m.free()
+            del m
+        except Exception as exc:   # a secondary row must never cost the headline line
+            rows.append({"workload": workload_string(name, shape, hole, emit, strategy), "error": repr(exc)[:300]})
+    return rows
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from pldepth_b200 import _lib, synth
-    from pldepth_b200.step import FusedPLStep
+    from pldepth_b200 import _lib
+    from pldepth_b200.dist import LossWindow
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,227 +470,161 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     shape = workload_shape(args.workload)
     B, H, W, K, R = shape["B"], shape["H"], shape["W"], shape["K"], shape["R"]
-    HW, L = H * W, B * R
-    n_sets = max(1, args.sets)
-    cfg_id = {"C1": 1, "C2": 2, "C3": 3, "C5s": 5, "C5": 5}[args.workload]
-
-    # synthetic maps: a few distinct rank-transformed fields, rolled to make B distinct images
-    base_maps = [synth.depth_map(H, W, 1000 * cfg_id + 17 * rank + i) for i in range(min(B, 4))]
-    gt_h = np.stack([np.roll(base_maps[b % len(base_maps)], 31 * b, axis=1) for b in range(B)])
-    mask_h = np.stack([synth.valid_mask(H, W, 3000 * cfg_id + b, args.hole) for b in range(B)])
-    rs = np.random.RandomState(2000 * cfg_id + rank)
-    pred_h = rs.standard_normal((B, H, W, 1)).astype(np.float32)
-
-    sets = []
-    for s in range(n_sets):
-        sets.append(dict(gt=torch.from_numpy(np.roll(gt_h, s, axis=0)).to(dev),
-                         mask=torch.from_numpy(mask_h).to(dev),
-                         pred=torch.from_numpy(np.roll(pred_h, s, axis=0)).to(dev),
-                         out=FusedPLStep.new_buffers(B, H, W, H, W, R, K, dev, emit_rankings=not args.no_emit)))
-    from pldepth_b200._lib import Context
-    step = FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B, emit_rankings=not args.no_emit)
-    # lanes: consecutive steps work on different buffer sets and do not depend on each other, so `lanes` of them
-    # are kept in flight on separate streams.  Lane 0 is the plain step on the current stream.
+    L = B * R
+    emit = not args.no_emit
     want_lanes = args.lanes if args.lanes is not None else (3 if L >= 100000 else 1)
-    n_lanes = 1 if args.graph else max(1, min(want_lanes, n_sets))
-    while n_sets % n_lanes:      # a buffer set must always be used by the same lane (stream order protects it)
-        n_lanes -= 1
-    lane_steps, lane_streams = [step], [torch.cuda.current_stream(dev)]
-    for l in range(1, n_lanes):
-        lane_steps.append(FusedPLStep(K, R, seed=cfg_id, global_batch=B * world, image_base=rank * B,
-                                      emit_rankings=not args.no_emit, context=Context(local_rank),
-                                      first_step=l << 24))
-        lane_streams.append(torch.cuda.Stream(dev))
-
-    pending = []
-
-    def one_step(i, lanes=1):
-        s = sets[i % n_sets]
-        lane = i % lanes
-        with torch.cuda.stream(lane_streams[lane]):
-            out = lane_steps[lane].run(s["gt"], s["mask"], s["pred"], out=s["out"])
-            if world > 1:
-                # the path's only exchange: one f64 per step.  Nothing downstream of the step depends on it
-                # (the gradient already carries the global 1/L), so it is issued asynchronously and overlaps
-                # the next step; every reduction is waited for before the timed region closes.
-                pending.append(dist.all_reduce(out["loss_sum"], async_op=True))
-                if len(pending) > n_sets - 1:
-                    pending.pop(0).wait()
-        return out
-
-    def fork_lanes(ev):
-        for st in lane_streams[1:]:
-            st.wait_event(ev)
-
-    def join_lanes():
-        cur = torch.cuda.current_stream(dev)
-        for st in lane_streams[1:]:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            cur.wait_event(ev)
-
-    def drain():
-        while pending:
-            pending.pop(0).wait()
+    m = Measurement(args.workload, shape, args.hole, emit, args.strategy, args.sets, want_lanes, world, rank,
+                    local_rank, graph=args.graph)
+    n_sets, n_lanes = m.n_sets, m.n_lanes
 
     for i in range(max(3, args.warmup)):
-        one_step(i, n_lanes)
-    drain()
-    torch.cuda.synchronize()
-    for ls in lane_steps:
-        ls.check(dev)
+        m.one_step(i)
+    m.barrier()
+    m.check()
 
     graphs = None
     if args.graph and world == 1:
         from pldepth_b200._lib import Context as _Ctx
-        _Ctx.current(local_rank).device_offset(True, step.step_index)   # fresh draws on every replay
+        _Ctx.current(local_rank).device_offset(True, m.lane_steps[0].step_index)   # fresh draws on every replay
         graphs = []
         for s in range(n_sets):
+            m.sets[s]["out"]["loss_sum"] = m.windows[0][0].slot(s)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                one_step(s)
+                m.lane_steps[0].run(m.sets[s]["gt"], m.sets[s]["mask"], m.sets[s]["pred"], out=m.sets[s]["out"])
             graphs.append(g)
         for g in graphs:
             g.replay()
         torch.cuda.synchronize()
 
-    def barrier():
-        drain()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- dominant kernel alone: the library records CUDA events around the list kernel of every
-    # step (pld_ctx_kernel_timing) on its launch stream, over a strictly sequential pass of the same steps
-    # (one lane: nothing else runs beside the kernel), taken BEFORE the timed region so that the power
+    # ---- dominant kernel alone, over a strictly sequential pass taken BEFORE the timed region so that the power
     # state left behind by the multi-lane burst cannot leak into it -----
-    ctx = Context.current(local_rank)
     n_k = max(5, min(args.steps, 50))
-    ctx.kernel_timing(n_k)
-    for i in range(n_k):
-        one_step(i)
-    drain()
-    torch.cuda.synchronize()
-    kms = ctx.kernel_times(n_k)
-    ctx.kernel_timing(0)
-    kms = sorted(kms)
-    k_ms = sum(kms) / len(kms)
+    k_ms, seq_ms = m.kernel_alone(n_k)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    red0 = m.reductions
     sampler.rows.clear()
-    e0.record()
-    fork_lanes(e0)
-    for i in range(args.steps):
-        if graphs is not None:
-            graphs[i % n_sets].replay()
-        else:
-            one_step(i, n_lanes)
-    join_lanes()
-    drain()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = m.timed(args.steps, graphs)
     launches = _lib.launch_count() - launches0
+    reductions = m.reductions - red0
     if graphs is not None:
         launches = args.steps * 3
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     # clocks under load: nvidia-smi needs ~50-100 ms per query and the timed region lasts only a few ms, so the
     # SAME steps keep running for ~0.7 s right after it while the sampler polls.  The burst length is derived
-    # from the max-reduced time, hence identical on every rank (each step carries a collective).
+    # from the max-reduced time, hence identical on every rank (the windows reduce collectively).
     n_burst = max(args.steps, min(20000, int(700.0 / max(ms_total / args.steps, 1e-3))))
     for i in range(n_burst):
         if graphs is not None:
             graphs[i % n_sets].replay()
         else:
-            one_step(i, n_lanes)
-    drain()
-    torch.cuda.synchronize()
+            m.one_step(i)
+    m.barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=3)
-    for ls in lane_steps:
-        ls.check(dev)
+    m.check()
+    clocks = sampler.summary()
 
     peak, peak_src = peaks()
-    abytes = algorithmic_bytes(B, HW, L, K)
-    achieved = abytes / (k_ms * 1e-3) / 1e9
+    roof = m.roofline(k_ms, ms_total / args.steps, seq_ms, peak, peak_src, clocks.get("sm_mhz"))
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
+            traffic = json.load(f).get(args.workload if emit and args.hole == 0 and args.strategy == "purely" else "-")
     except Exception:
         pass
+    roof["traffic"] = traffic
 
     # ---- end to end through the public API with HOST buffers ---------------------------------
     # HostPipelinedStep: every step copies its gt / mask / pred from pinned host memory, runs the
     # fused step and copies loss + dense gradient back; copies of neighbouring steps overlap kernels.
+    # At N > 1 the per-step loss sums go through a LossWindow: one all-reduce + one D2H of the reduced
+    # window close the timed region, so the loss that reaches the host is the GLOBAL one.
     from pldepth_b200.step import HostPipelinedStep
-    gt_p = [torch.from_numpy(np.roll(gt_h, s, axis=0)).pin_memory() for s in range(2)]
-    mask_p = torch.from_numpy(mask_h).pin_memory()
-    pred_p = [torch.from_numpy(np.roll(pred_h, s, axis=0)).pin_memory() for s in range(2)]
-    runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B,
-                               emit_rankings=not args.no_emit)
-
-    def e2e_step(i):
-        t = runner.submit(gt_p[i % 2], mask_p, pred_p[i % 2])
-        if world > 1:
-            dist.all_reduce(runner.slots[t % 2]["out"]["loss_sum"])
-        return t
-
+    gt_h, mask_h, pred_h = m.gt_h, m.mask_h, m.pred_h
+    cfg_id = m.cfg_id
     n_e2e = max(3, min(args.steps, 20))
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    last = 0
-    for i in range(n_e2e):
-        last = e2e_step(i)
-    loss_host, grad_host = runner.result(last)          # waits for the final D2H
-    b_.record()
-    barrier()
-    ms_e2e = a.elapsed_time(b_)
-    if world > 1:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    h2d, d2h = runner.bytes_per_step()
-    e2e = {"value": L * world * n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
-           "api": "HostPipelinedStep.submit/result: pinned host gt+mask+pred -> device, fused step, loss + dense "
-                  "gradient -> pinned host; 2 slots, H2D / compute / D2H streams overlap across steps",
-           "last_loss": loss_host, "host_numa": numa}
+
+    def e2e_leg(mask_dtype):
+        gt_p = [torch.from_numpy(np.roll(gt_h, s, axis=0)).pin_memory() for s in range(2)]
+        mask_src = mask_h.astype(np.uint8) if mask_dtype == torch.uint8 else mask_h
+        mask_p = torch.from_numpy(mask_src).pin_memory()
+        pred_p = [torch.from_numpy(np.roll(pred_h, s, axis=0)).pin_memory() for s in range(2)]
+        runner = HostPipelinedStep(K, R, B, H, W, seed=cfg_id, global_batch=B * world, image_base=rank * B,
+                                   emit_rankings=emit, mask_dtype=mask_dtype)
+        window = LossWindow(n_e2e, dev)
+        h_window = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
+
+        def e2e_step(i, record):
+            sl = runner.slots[runner.count % len(runner.slots)]
+            if record:
+                sl["out"]["loss_sum"] = window.slot(i)
+            return runner.submit(gt_p[i % 2], mask_p, pred_p[i % 2])
+
+        for i in range(3):
+            e2e_step(i, False)
+        m.barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = 0
+        for i in range(n_e2e):
+            last = e2e_step(i, True)
+            window.mark()
+        loss_host, grad_host = runner.result(last)          # waits for the final D2H (local loss + dense gradient)
+        window.reduce()                                     # N > 1: the one collective of the leg
+        h_window.copy_(window.values(), non_blocking=True)
+        b_.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            loss_host = float(h_window[-1]) / float(B * world * R)
+        m.barrier()
+        ms = a.elapsed_time(b_)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        h2d, d2h = runner.bytes_per_step()
+        return {"value": L * world * n_e2e / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h) + 8, "ms_per_step": ms / n_e2e, "steps": n_e2e,
+                "last_loss": loss_host, "loss_is_global": True}
+
+    e2e = e2e_leg(torch.float32)
+    e2e["api"] = ("HostPipelinedStep.submit/result: pinned host gt+mask+pred (float32) -> device, fused step, loss + "
+                  "dense gradient -> pinned host; 2 slots, H2D / compute / D2H streams overlap across steps; at N>1 "
+                  "the per-step loss sums are all-reduced once (LossWindow) and read back inside the timed region")
+    e2e["host_numa"] = numa
+    e2e_u8 = None
+    if args.strategy == "purely":
+        e2e_u8 = e2e_leg(torch.uint8)
+        e2e_u8["api"] = "same, mask handed over as uint8 (nonzero = valid; pld_fused_step_m8): a quarter of the mask bytes"
+
+    secondary = None
+    if world == 1 and args.secondary:
+        m.free()
+        secondary = secondary_rows(world, rank, local_rank, peak, peak_src, clocks.get("sm_mhz"))
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": L * world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s per GPU: B=%d images %dx%d, ranking_size K=%d, R=%d lists/image, %s "
-                                   "mask, core sampler (factor 1.0), rankings %s" % (
-                                       args.workload, B, H, W, K, R,
-                                       "all-ones" if args.hole == 0 else "%.0f%%-hole" % (100 * args.hole),
-                                       "not materialised" if args.no_emit else "emitted"),
+            "config": {"workload": workload_string(args.workload, shape, args.hole, emit, args.strategy),
                        "lists_per_step": L * world, "sharding": "per image, %d GPU(s)" % world,
                        "cache": "rotating %d input/output buffer sets of %.0f MB each (> 126 MB L2), no reuse "
-                                "between consecutive steps" % (n_sets, abytes / 1e6),
+                                "between consecutive steps" % (n_sets, roof["algorithmic_bytes"] / 1e6),
                        "cuda_graph": bool(graphs),
                        "lanes": "%d independent batches in flight on separate streams (own lookup tables each); "
-                                "roofline.kernel_ms is timed in a separate sequential pass" % n_lanes},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic,
-                         "kernel": ("lists_small_kernel<K,PHILOX_TAB,LOSS>" if K <= 16 else
-                                    "lists_large_kernel<LPL,IPL,PHILOX_TAB,LOSS>") +
-                                   " (fused sample+order+emit+gather+loss+bwd)",
-                         "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+                                "roofline.kernel_ms is timed in a separate sequential pass" % n_lanes,
+                       "collective": "loss sums all-reduced once per %d steps per lane (LossWindow), %d all-reduce(s) "
+                                     "inside the timed region" % (m.window_steps, reductions)},
+            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if e2e_u8 is not None:
+            line["e2e_u8_mask"] = e2e_u8
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_rate_single(shape, args.cpu_seconds)
         print(json.dumps(line))

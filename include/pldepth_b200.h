@@ -209,6 +209,15 @@ int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float
                    float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
                    float* per_list, float* grad, void* stream);
 
+/* The same call for a uint8 mask (nonzero = valid pixel), the form the reference's consistency masks have on disk
+ * (HR-WSI valid_masks are 8-bit PNGs, pldepth/data/dao/hr_wsi.py:55-83, cast to float by the tf.data pipeline): a host
+ * caller ships a quarter of the mask bytes, everything else is identical to pld_fused_step.
+ *   mask u8[B,Hm,Wm] */
+int pld_fused_step_m8(pld_ctx* ctx, const uint8_t* mask, const float* gt, const float* pred, int B, int Hm,
+                      int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
+                      float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
+                      float* per_list, float* grad, void* stream);
+
 /* Same step for the score-based strategies (Masked / Thresholded / InformationScore,
  * sampling.py:157-169, 190-208, 218-239): n = int(R * factor) Philox candidate lists per image are drawn
  * and scored (only the 8-byte ordered score is stored), the best R are ordered by score descending (ties:

@@ -51,6 +51,26 @@ __device__ __forceinline__ uint32_t flags16(const float* __restrict__ m, int bas
   return f;
 }
 
+// same for a uint8 mask (nonzero = valid): 16 pixels = one 16-byte load
+__device__ __forceinline__ uint32_t flags16(const uint8_t* __restrict__ m, int base, int Nm) {
+  uint32_t f = 0;
+  if (base + PC_ITEMS <= Nm && ((reinterpret_cast<uintptr_t>(m + base) & 15) == 0)) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(m + base));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f |= (((w[q] >> (8 * j)) & 0xFFu) ? 1u : 0u) << (q * 4 + j);
+  } else {
+#pragma unroll
+    for (int i = 0; i < PC_ITEMS; ++i)
+      if (base + i < Nm && __ldg(m + base + i) != 0) f |= 1u << i;
+  }
+  return f;
+}
+__device__ __forceinline__ bool mask_on(float v) { return v > 0.f; }      // np.where(mask > 0), sampling.py:135
+__device__ __forceinline__ bool mask_on(uint8_t v) { return v != 0; }
+
 __device__ __forceinline__ int block_sum_int(int v, int* s_warp) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -63,13 +83,14 @@ __device__ __forceinline__ int block_sum_int(int v, int* s_warp) {
   return t;
 }
 
-__global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const float* __restrict__ mask, int Nm, int nchunks,
+template <typename MT>
+__global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __restrict__ mask, int Nm, int nchunks,
                                                                int* __restrict__ counts, float4* __restrict__ grad4,
                                                                size_t grad_n4, float* __restrict__ grad_tail,
                                                                int grad_tail_n) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const float* m = mask + (size_t)b * Nm;
+  const MT* m = mask + (size_t)b * Nm;
   const int base = chunk * PC_CHUNK + threadIdx.x * PC_ITEMS;
   const int c = (base < Nm) ? __popc(flags16(m, base, Nm)) : 0;
   const int tot = block_sum_int(c, s_warp);
@@ -82,8 +103,9 @@ __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const float* __r
   }
 }
 
+template <typename MT>
 __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
-    const float* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
+    const MT* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
     int W, int HW, double xs, double ys, int identity_scale, int nchunks, const int* __restrict__ counts,
     float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid, int32_t* __restrict__ vj_flat,
     float* __restrict__ grad_valid) {
@@ -139,7 +161,7 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   // Compaction with lane-consecutive pixels: warp w of the CTA owns pixels
   // [chunk*CHUNK + w*512, +512) as 16 rows of 32; ballots give each valid pixel its rank, so mask
   // reads, gt reads and table writes are all coalesced.
-  const float* m = mask + (size_t)b * Nm;
+  const MT* m = mask + (size_t)b * Nm;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wbase = chunk * PC_CHUNK + wid * (PC_ITEMS * 32);
   uint32_t bal[PC_ITEMS];
@@ -147,7 +169,7 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
 #pragma unroll
   for (int i = 0; i < PC_ITEMS; ++i) {
     const int idx = wbase + i * 32 + lane;
-    const bool v = (idx < Nm) && (__ldg(m + idx) > 0.f);
+    const bool v = (idx < Nm) && mask_on(__ldg(m + idx));
     bal[i] = __ballot_sync(0xffffffffu, v);
     wcount += __popc(bal[i]);
   }
@@ -543,7 +565,8 @@ using namespace pld;
 
 // Passes 1-2 of both fused steps: valid pixels counted per chunk while `grad` is zeroed, then the per-image lookup
 // tables (layouts: see prep_build_kernel).
-static int launch_prep(const float* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
+template <typename MT>
+static int launch_prep(const MT* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
                        int* counts, float2* table, size_t tstride, int32_t* nv, int32_t* vj_flat, float* grad_valid,
                        float* grad, cudaStream_t st) {
   const int HW = H * W, Nm = Hm * Wm;
@@ -559,20 +582,21 @@ static int launch_prep(const float* mask, const float* gt, const float* pred, in
     n4 = gtotal / 4;
     tail = (int)(gtotal - n4 * 4);
   }
-  prep_count_kernel<<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
+  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
   PLD_CHECK_LAUNCH();
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
-  prep_build_kernel<<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
+  prep_build_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
                                                 table, tstride, nv, vj_flat, grad_valid);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
 
-extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
-                              int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
-                              float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
-                              float* per_list, float* grad, void* stream) {
+template <typename MT>
+static int fused_step_impl(pld_ctx* ctx, const MT* mask, const float* gt, const float* pred, int B, int Hm,
+                           int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
+                           float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
+                           float* per_list, float* grad, void* stream) {
   PLD_REQUIRE(ctx && mask && gt && pred && loss, "null argument");
   PLD_CHECK_DEVICE(ctx);
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
@@ -642,6 +666,22 @@ extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, 
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   if (rc == PLD_OK && ctx->use_device_offset) rc = launch_offset_advance(ctx, st);
   return rc;
+}
+
+extern "C" int pld_fused_step(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
+                              int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
+                              float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
+                              float* per_list, float* grad, void* stream) {
+  return fused_step_impl<float>(ctx, mask, gt, pred, B, Hm, Wm, H, W, K, n, seed, offset, image_base, scale, n_valid,
+                                rankings, loss, loss_sum, per_list, grad, stream);
+}
+
+extern "C" int pld_fused_step_m8(pld_ctx* ctx, const uint8_t* mask, const float* gt, const float* pred, int B, int Hm,
+                                 int Wm, int H, int W, int K, int n, uint64_t seed, uint64_t offset, int image_base,
+                                 float scale, int32_t* n_valid, float* rankings, float* loss, double* loss_sum,
+                                 float* per_list, float* grad, void* stream) {
+  return fused_step_impl<uint8_t>(ctx, mask, gt, pred, B, Hm, Wm, H, W, K, n, seed, offset, image_base, scale, n_valid,
+                                  rankings, loss, loss_sum, per_list, grad, stream);
 }
 
 extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,

@@ -73,7 +73,13 @@ class FusedPLStep(object):
         shape the call declares.  Dtype / layout mismatches of the inputs are converted (a copy); anything
         that cannot be fixed by a conversion raises."""
         gt = ops.as_cuda(gt, torch.float32, "gt")
-        mask = ops.as_cuda(mask, torch.float32, "mask")
+        # masks stay uint8 when they arrive as uint8 / bool (nonzero = valid; pld_fused_step_m8), else float32
+        m_dtype = getattr(mask, "dtype", None)
+        if m_dtype == torch.bool:
+            mask = mask.to(torch.uint8)
+        mask = ops.as_cuda(mask, torch.uint8 if m_dtype in (torch.uint8, torch.bool) else torch.float32, "mask")
+        if mask.dtype == torch.uint8 and self.strategy != "purely":
+            mask = mask.to(torch.float32)          # the scored step takes float masks only
         pred = ops.as_cuda(pred, torch.float32, "pred")
         if gt.dim() == 4 and gt.shape[-1] == 1:
             gt = gt[..., 0].contiguous()
@@ -146,10 +152,11 @@ class FusedPLStep(object):
             self.step_index += 1
             return buf
         # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
-        check(lib.pld_fused_step(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
-                                 self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
-                                 p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),
-                                 p(buf["grad"]), stream))
+        entry = lib.pld_fused_step_m8 if mask.dtype == torch.uint8 else lib.pld_fused_step
+        check(entry(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
+                    self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
+                    p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),
+                    p(buf["grad"]), stream))
         self.step_index += 1
         return buf
 
@@ -159,9 +166,10 @@ class FusedPLStep(object):
         copying into the same gt / mask / pred tensors.  Returns (graph, output buffers).  While a captured step
         is in use, other Philox calls on this thread's context share (and advance) the same device counter."""
         for name, t in (("gt", gt), ("mask", mask), ("pred", pred)):
-            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-                raise ValueError("capture(): %s must already be a contiguous float32 CUDA tensor (a converted copy "
-                                 "would be frozen into the graph)" % name)
+            ok_dtype = (torch.float32, torch.uint8) if name == "mask" else (torch.float32,)
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in ok_dtype and t.is_contiguous()):
+                raise ValueError("capture(): %s must already be a contiguous float32 (mask: or uint8) CUDA tensor (a "
+                                 "converted copy would be frozen into the graph)" % name)
         dev = gt.device
         ctx = self._ctx if self._ctx is not None else Context.current(dev.index or 0)
         ctx.device_offset(True, self.step_index)
@@ -204,7 +212,9 @@ class HostPipelinedStep(object):
     """
 
     def __init__(self, ranking_size, rankings_per_image, B, H, W, Hm=None, Wm=None, seed=0, device=None,
-                 emit_rankings=True, global_batch=None, image_base=0, slots=2):
+                 emit_rankings=True, global_batch=None, image_base=0, slots=2, mask_dtype=torch.float32):
+        """``mask_dtype``: torch.float32 (what the reference's pipeline hands over) or torch.uint8 (the masks as they
+        are stored, nonzero = valid: a quarter of the mask bytes cross PCIe; the kernels read them directly)."""
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         Hm, Wm = Hm or H, Wm or W
         self.dev = dev
@@ -214,28 +224,29 @@ class HostPipelinedStep(object):
         for _ in range(slots):
             self.slots.append(dict(
                 gt=torch.empty((B, H, W), dtype=torch.float32, device=dev),
-                mask=torch.empty((B, Hm, Wm), dtype=torch.float32, device=dev),
+                mask=torch.empty((B, Hm, Wm), dtype=mask_dtype, device=dev),
                 pred=torch.empty((B, H, W, 1), dtype=torch.float32, device=dev),
                 out=FusedPLStep.new_buffers(B, H, W, Hm, Wm, rankings_per_image, ranking_size, dev, emit_rankings),
                 h_loss=torch.empty(1, dtype=torch.float32).pin_memory(),
                 h_grad=torch.empty((B, H, W, 1), dtype=torch.float32).pin_memory(),
                 ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), used=False))
+        self.mask_dtype = mask_dtype
         self.s_in = torch.cuda.Stream(dev)
         self.s_out = torch.cuda.Stream(dev)
         self.count = 0
 
     @staticmethod
-    def _host(x):
+    def _host(x, dtype=torch.float32):
         if isinstance(x, torch.Tensor):
-            return x
+            return x if x.dtype == dtype else x.to(dtype)
         import numpy as np
-        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if dtype == torch.uint8 else np.float32))
 
     def submit(self, gt, mask, pred):
         i = self.count
         sl = self.slots[i % len(self.slots)]
         compute = torch.cuda.current_stream(self.dev)
-        gt, mask, pred = self._host(gt), self._host(mask), self._host(pred)
+        gt, mask, pred = self._host(gt), self._host(mask, self.mask_dtype), self._host(pred)
         with torch.cuda.stream(self.s_in):
             if sl["used"]:
                 self.s_in.wait_event(sl["ev_done"])      # the slot's previous kernels have consumed the inputs
@@ -268,4 +279,5 @@ class HostPipelinedStep(object):
 
     def bytes_per_step(self):
         B, H, W, Hm, Wm = self.shape
-        return (2 * B * H * W + B * Hm * Wm) * 4, (B * H * W + 1) * 4
+        mask_bytes = B * Hm * Wm * (1 if self.mask_dtype == torch.uint8 else 4)
+        return 2 * B * H * W * 4 + mask_bytes, (B * H * W + 1) * 4

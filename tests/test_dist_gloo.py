@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from oracle import listmle_oracle as lo
 from oracle import sampler_oracle as so
-from pldepth_b200.dist import ShardedPLStep, shard_bounds
+from pldepth_b200.dist import LossWindow, ShardedPLStep, shard_bounds
 
 B, H, W, K, R = 5, 12, 10, 4, 30
 
@@ -53,6 +53,54 @@ def worker(rank, world, port, out_dir):
                  lo=lo_, hi=hi_)
     finally:
         dist.destroy_process_group()
+
+
+def window_worker(rank, world, port, out_dir):
+    """Three steps with loss_every=2: one full window (reduced inside run) + one flushed partial window."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gt, mask, pred = make_inputs()
+        step = ShardedPLStep(K, R, B, local_step=oracle_local_step, loss_every=2)
+        lo_, hi_ = step.lo, step.hi
+        got = []
+        for i in range(3):
+            p = pred * (1.0 + 0.5 * i)
+            out = step.run(torch.from_numpy(gt[lo_:hi_]), torch.from_numpy(mask[lo_:hi_]), torch.from_numpy(p[lo_:hi_]))
+            if i == 0:
+                assert out["loss"] is None and out["losses"] is None
+            if i == 1:
+                assert out["losses"].numel() == 2
+                got += out["losses"].tolist()
+        got += step.flush().tolist()
+        assert step.flush() is None
+        np.save(os.path.join(out_dir, "win%d.npy" % rank), np.array(got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loss_window_reduces_once_per_n_steps(tmp_path):
+    world = 2
+    mp.spawn(window_worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    gt, mask, pred = make_inputs()
+    want = []
+    for i in range(3):
+        single = oracle_local_step(torch.from_numpy(gt), torch.from_numpy(mask), torch.from_numpy(pred * (1.0 + 0.5 * i)), 0, B)
+        want.append(single["loss_sum"].item() / (B * R))
+    w0, w1 = np.load(tmp_path / "win0.npy"), np.load(tmp_path / "win1.npy")
+    assert np.array_equal(w0, w1) and w0.shape == (3,)
+    assert np.allclose(w0, want, rtol=1e-6)
+
+
+def test_loss_window_without_process_group():
+    w = LossWindow(3, "cpu")
+    for i in range(3):
+        w.slot(i).fill_(float(i + 1))
+        full = w.mark()
+    assert full and w.reduce() is None and w.values().tolist() == [1.0, 2.0, 3.0]
+    with pytest.raises(ValueError):
+        LossWindow(0, "cpu")
 
 
 def free_port():

@@ -454,3 +454,24 @@ def test_full_size_config3_and_config5_properties(cuda_device, name, B, H, W, K,
     hist = torch.bincount((idx[b].reshape(-1) * 64) // (H * W), minlength=64).double()
     exp = R * K / 64.0
     assert float(((hist - exp).abs() / exp ** 0.5).max()) < 6.0
+
+
+import glob as _glob
+import os as _os
+
+TFR_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "listmle_*.npz")))
+
+
+@pytest.mark.skipif(not TFR_GOLDEN, reason="no tests/golden/listmle_*.npz yet (run tools/pin_tfranking.py where TF exists)")
+@pytest.mark.parametrize("path", TFR_GOLDEN, ids=[_os.path.basename(p)[8:-4] for p in TFR_GOLDEN])
+def test_cuda_loss_matches_tfranking_goldens(cuda_device, path):
+    """The CUDA loss against outputs of the reference's own HourglassNegativeLogLikelihood (tools/pin_tfranking.py)."""
+    from pldepth_b200.losses import HourglassNegativeLogLikelihood
+    g = np.load(path)
+    B, K = int(g["batch_size"]), int(g["ranking_size"])
+    yt = torch.from_numpy(g["y_true"]).to(cuda_device)
+    yp = torch.from_numpy(g["y_pred"]).to(cuda_device).requires_grad_(True)
+    value = HourglassNegativeLogLikelihood(K, B)(yt, yp)
+    value.backward()
+    assert_close(value.item(), float(g["loss"]), "loss vs TF-Ranking")
+    assert_close(yp.grad.cpu().numpy(), g["grad"], "gradient vs TF-Ranking")

@@ -106,3 +106,52 @@ def test_full_loss_mean_scatter_and_duplicates():
     assert abs(ls - loss * B * R) < 1e-9 and np.allclose(gs, grad * B * R)
     lg, gg, _ = lo.hourglass_nll(y_true, pred, B, K, global_lists=4 * B * R)
     assert abs(lg - loss / 4) < 1e-12 and np.allclose(gg, grad / 4)
+
+
+# ---- pin against the real TF-Ranking binary (files exist only after tools/pin_tfranking.py has run somewhere with
+# TensorFlow + tensorflow_ranking==0.3.1; until then the oracle stays "parity unpinned") -------------------------------
+import glob
+import importlib.util
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+TFR_GOLDEN = sorted(glob.glob(os.path.join(_HERE, "golden", "listmle_*.npz")))
+
+
+def _pin_module():
+    spec = importlib.util.spec_from_file_location("pin_tfranking", os.path.join(_HERE, "..", "tools", "pin_tfranking.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_pin_generator_cases_are_deterministic_and_tie_free():
+    """The golden generator's inputs (NumPy part, no TensorFlow needed): reproducible, labels distinct per list except
+    the injected invalid ones, indices inside the map -- and the oracle runs on every case."""
+    pin = _pin_module()
+    a, b = pin.make_cases(), pin.make_cases()
+    assert list(a) == list(b) and len(a) >= 8
+    for name, c in a.items():
+        assert np.array_equal(c["y_true"], b[name]["y_true"]) and np.array_equal(c["y_pred"], b[name]["y_pred"])
+        B, K = c["batch_size"], c["ranking_size"]
+        y = c["y_true"].reshape(-1, K, 2)
+        assert y[..., 0].min() >= 0 and y[..., 0].max() < c["y_pred"].size // B
+        for row in y[..., 1]:
+            v = row[row >= 0]
+            assert len(np.unique(v)) == len(v), name
+        loss, grad, per_list = lo.hourglass_nll(c["y_true"], c["y_pred"], B, K)
+        assert np.isfinite(loss) and np.isfinite(grad).all() and per_list.shape[0] == y.shape[0]
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(not TFR_GOLDEN, reason="no tests/golden/listmle_*.npz yet (run tools/pin_tfranking.py where TF exists)")
+@pytest.mark.parametrize("path", TFR_GOLDEN, ids=[os.path.basename(p)[8:-4] for p in TFR_GOLDEN])
+def test_oracle_matches_tfranking_goldens(path):
+    g = np.load(path)
+    B, K = int(g["batch_size"]), int(g["ranking_size"])
+    loss, grad, per_list = lo.hourglass_nll(g["y_true"], g["y_pred"], B, K, dtype=np.float32)
+    assert abs(loss - float(g["loss"])) <= 1e-6 * max(abs(float(g["loss"])), 1e-12)
+    assert np.abs(per_list - g["per_list"]).max() <= 1e-6 * np.abs(g["per_list"]).max()
+    assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()

@@ -246,6 +246,24 @@ int pld_ordinal_error(pld_ctx* ctx, const float* pred, const float* gt, const in
 int pld_ndcg(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* ids, int N, int HW, int n, float* out,
              void* stream);
 
+/* ---- evaluation list generators, bit-compatible with the NumPy global stream ---------------
+ * GenericHourglassPairRelationDataProvider.generate_ordinal_pairs (pldepth/data/providers/generic_ranking_provider.py:
+ * 80-111): per image n_pairs pairs; each pair draws x0 = randint(H), y0 = randint(W), x1 = randint(H), y1 = randint(W)
+ * (masked rejection on raw MT19937 words with ALTERNATING bounds, consumed from word *consumed_io on, which is
+ * advanced); row = (x0*W + y0, x1*W + y1, get_depth_relation(z0, z1, threshold) [negated if invert_sign], z0, z1) as
+ * float32.  threshold < 0 = the reference's threshold=None (plain comparison).  Raises PLD_ST_MT_EXHAUSTED when the
+ * stream is too short.
+ *   gt f32[N,H*W], raw u32[n_raw], consumed_io i64[1] (device, in/out) -> pairs_out f32[N,n_pairs,5] */
+int pld_eval_ordinal_pairs_mt(pld_ctx* ctx, const float* gt, int N, int H, int W, int n_pairs, double threshold,
+                              int invert_sign, int promotion, const uint32_t* raw, int64_t n_raw, int64_t* consumed_io,
+                              float* pairs_out, void* stream);
+/* GenericHourglassRankingDataProvider.generate_rankings (generic_ranking_provider.py:180-215) draws and orders its
+ * lists exactly like the core sampler on a full mask (pld_sample_lists_mt with the identity table); with
+ * invert_relation_sign it stores them by original depth ASCENDING with depth -> 1 / (depth + 1): this call applies
+ * that transformation in place to depth-descending lists.
+ *   rankings f32[n_lists,K,2] in/out */
+int pld_eval_invert_rankings(pld_ctx* ctx, float* rankings, int64_t n_lists, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,9 @@ SIGNATURES = {
                                        c_void_p]),
     "pld_ordinal_error": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
+    "pld_eval_ordinal_pairs_mt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p,
+                                          c_i64, c_void_p, c_void_p, c_void_p]),
+    "pld_eval_invert_rankings": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "pld_ndcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

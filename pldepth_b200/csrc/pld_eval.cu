@@ -1,6 +1,7 @@
 // Evaluation metrics that sit right of the training step: same
 // gather-compare-reduce pattern as the loss.  One CTA per image.
 #include "pld_common.cuh"
+#include "pld_score.cuh"
 
 namespace pld {
 
@@ -132,6 +133,124 @@ __global__ void __launch_bounds__(256) gather_predictions_kernel(const float2* _
   if (bad) atomicOr(status, bad);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Evaluation list generators (pldepth/data/providers/generic_ranking_provider.py:80-111, 180-215), MT19937-compatible.
+//
+// generate_ordinal_pairs draws, per pair, x0 = randint(H), y0 = randint(W), x1 = randint(H), y1 = randint(W) from the
+// global NumPy stream: masked rejection with a bound that ALTERNATES between H and W.  Whether a raw word is accepted
+// therefore depends on the parity of the draws accepted before it -- a two-state automaton.  One warp walks the
+// stream 32 words at a time and composes the per-word transition functions with a shuffle scan
+// (state -> (next state, accepted count)), so every lane knows the bound that applies to its word and the rank of its
+// draw.  Evaluation lists are generated once per dataset (the reference caches them to .npy), so one warp is enough:
+// about 1 M draws per 4 ms.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t np_mask_eval(uint32_t M) {  // smallest 2^k - 1 >= M - 1
+  const uint32_t r = M - 1u;
+  return r == 0 ? 0u : (0xFFFFFFFFu >> __clz(r));
+}
+
+__global__ void __launch_bounds__(32) mt_alternating_draws_kernel(const uint32_t* __restrict__ raw, long long n_raw,
+                                                                  long long* __restrict__ consumed_io, uint32_t M0,
+                                                                  uint32_t M1, long long need, int32_t* __restrict__ draws,
+                                                                  int* status) {
+  const int lane = threadIdx.x;
+  const uint32_t m0 = np_mask_eval(M0), m1 = np_mask_eval(M1);
+  long long p = *consumed_io, rank = 0, last = -1;
+  int S = 0;
+  while (rank < need && p < n_raw) {
+    const long long idx = p + lane;
+    const bool valid = idx < n_raw;
+    const uint32_t w = valid ? __ldg(raw + idx) : 0u;
+    const int a0 = (valid && (w & m0) <= M0 - 1u) ? 1 : 0, a1 = (valid && (w & m1) <= M1 - 1u) ? 1 : 0;
+    // transition function of this word: from state s go to s ^ a_s, having accepted a_s draws
+    int e0 = a0, e1 = 1 ^ a1, n0 = a0, n1 = a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int pe0 = __shfl_up_sync(0xffffffffu, e0, o), pe1 = __shfl_up_sync(0xffffffffu, e1, o);
+      const int pn0 = __shfl_up_sync(0xffffffffu, n0, o), pn1 = __shfl_up_sync(0xffffffffu, n1, o);
+      if (lane >= o) {   // compose: the earlier segment first, then this one
+        const int ne0 = pe0 ? e1 : e0, ne1 = pe1 ? e1 : e0;
+        const int nn0 = pn0 + (pe0 ? n1 : n0), nn1 = pn1 + (pe1 ? n1 : n0);
+        e0 = ne0; e1 = ne1; n0 = nn0; n1 = nn1;
+      }
+    }
+    // exclusive prefix = inclusive of the lane before (identity for lane 0)
+    int xe0 = __shfl_up_sync(0xffffffffu, e0, 1), xe1 = __shfl_up_sync(0xffffffffu, e1, 1);
+    int xn0 = __shfl_up_sync(0xffffffffu, n0, 1), xn1 = __shfl_up_sync(0xffffffffu, n1, 1);
+    if (lane == 0) { xe0 = 0; xe1 = 1; xn0 = 0; xn1 = 0; }
+    const int st = S ? xe1 : xe0;
+    const long long r = rank + (S ? xn1 : xn0);
+    const bool acc = st ? (a1 != 0) : (a0 != 0);
+    if (acc && r < need) {
+      draws[r] = (int32_t)(w & (st ? m1 : m0));
+      if (r == need - 1) last = idx + 1;
+    }
+    const int te0 = __shfl_sync(0xffffffffu, e0, 31), te1 = __shfl_sync(0xffffffffu, e1, 31);
+    const int tn0 = __shfl_sync(0xffffffffu, n0, 31), tn1 = __shfl_sync(0xffffffffu, n1, 31);
+    rank += S ? tn1 : tn0;
+    S = S ? te1 : te0;
+    p += 32;
+  }
+  // the lane that produced the last needed draw knows where the stream stands
+  long long end = last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long t = __shfl_xor_sync(0xffffffffu, end, o);
+    end = t > end ? t : end;
+  }
+  if (lane == 0) {
+    if (need > 0 && end < 0) { atomicOr(status, PLD_ST_MT_EXHAUSTED); end = n_raw; }
+    if (need > 0) *consumed_io = end;
+  }
+}
+
+// get_depth_relation (depth_utils.py:5-21) with NumPy's scalar promotion: +1 / -1 / 0
+template <typename T>
+__device__ __forceinline__ int depth_relation(float z0, float z1, bool thresholded, const ScoreCfg& C) {
+  if (!thresholded) return z0 > z1 ? 1 : (z0 < z1 ? -1 : 0);
+  if (sizeof(T) == 4) {
+    const float r = __fdiv_rn(__fadd_rn(z0, 1e-10f), __fadd_rn(z1, 1e-10f));
+    return r >= C.thr_hi_f ? 1 : (r <= C.thr_lo_f ? -1 : 0);
+  }
+  const double r = __ddiv_rn(__dadd_rn((double)z0, 1e-10), __dadd_rn((double)z1, 1e-10));
+  return r >= C.thr_hi ? 1 : (r <= C.thr_lo ? -1 : 0);
+}
+
+__global__ void __launch_bounds__(256) ordinal_pairs_kernel(const float* __restrict__ gt, const int32_t* __restrict__ draws,
+                                                            int W, int HW, long long per_image, long long total,
+                                                            int thresholded, int invert, ScoreCfg C,
+                                                            float* __restrict__ out) {
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < total; q += (long long)gridDim.x * 256) {
+    const long long b = q / per_image;
+    const int x0 = draws[4 * q + 0], y0 = draws[4 * q + 1], x1 = draws[4 * q + 2], y1 = draws[4 * q + 3];
+    const int p0 = x0 * W + y0, p1 = x1 * W + y1;
+    const float z0 = __ldg(gt + b * HW + p0), z1 = __ldg(gt + b * HW + p1);
+    int rel = (C.promotion == PLD_PROMOTION_NEP50) ? depth_relation<float>(z0, z1, thresholded != 0, C)
+                                                   : depth_relation<double>(z0, z1, thresholded != 0, C);
+    if (invert) rel = -rel;
+    float* o = out + 5 * q;
+    o[0] = (float)p0; o[1] = (float)p1; o[2] = (float)rel; o[3] = z0; o[4] = z1;
+  }
+}
+
+// generate_rankings with invert_relation_sign (generic_ranking_provider.py:200-206): lists ordered by ORIGINAL depth
+// ascending (= the descending order reversed, ties: earlier draw first) and depths stored as 1 / (d + 1) (float64
+// arithmetic, rounded once to float32).  In place, one thread per (list, mirrored pair of positions).
+__global__ void __launch_bounds__(256) invert_rankings_kernel(float2* __restrict__ rk, long long n_lists, int K) {
+  const int half = (K + 1) / 2;
+  const long long total = n_lists * half;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const long long l = t / half;
+    const int i = (int)(t - l * half), j = K - 1 - i;
+    float2* row = rk + l * K;
+    const float2 a = row[i], c = row[j];
+    const float2 ai = make_float2(a.x, (float)(1.0 / ((double)a.y + 1.0)));
+    const float2 ci = make_float2(c.x, (float)(1.0 / ((double)c.y + 1.0)));
+    row[j] = ai;
+    if (i != j) row[i] = ci;
+  }
+}
+
 }  // namespace pld
 
 using namespace pld;
@@ -172,6 +291,46 @@ int pld_ndcg(pld_ctx* ctx, const float* pred, const float* gt, const int32_t* id
   while (p2 < n) p2 <<= 1;
   ndcg_kernel<<<N, 256, sizeof(float) * 2 * (size_t)p2, (cudaStream_t)stream>>>(pred, gt, ids, HW, n, p2, out,
                                                                               ctx->d_status);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+int pld_eval_ordinal_pairs_mt(pld_ctx* ctx, const float* gt, int N, int H, int W, int n_pairs, double threshold,
+                              int invert_sign, int promotion, const uint32_t* raw, int64_t n_raw, int64_t* consumed_io,
+                              float* pairs_out, void* stream) {
+  PLD_REQUIRE(ctx && gt && raw && consumed_io && pairs_out, "null argument");
+  PLD_CHECK_DEVICE(ctx);
+  PLD_REQUIRE(N > 0 && n_pairs >= 0 && n_raw >= 0, "bad shape");
+  PLD_REQUIRE(H > 1 && W > 1 && (long long)H * W <= PLD_MAX_PIXELS, "maps must be at least 2 x 2 (randint(1) consumes no word)");
+  PLD_REQUIRE(promotion == PLD_PROMOTION_NEP50 || promotion == PLD_PROMOTION_LEGACY, "bad promotion");
+  const long long total = (long long)N * n_pairs;
+  if (total == 0) return PLD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ctx->ensure_scratch(sizeof(int32_t) * 4 * (size_t)total);
+  if (rc) return rc;
+  int32_t* draws = (int32_t*)ctx->d_scratch;
+  mt_alternating_draws_kernel<<<1, 32, 0, st>>>(raw, (long long)n_raw, (long long*)consumed_io, (uint32_t)H, (uint32_t)W,
+                                                4 * total, draws, ctx->d_status);
+  PLD_CHECK_LAUNCH();
+  const bool thresholded = threshold >= 0.0;          // negative = the reference's threshold=None (plain comparison)
+  const ScoreCfg C = make_score_cfg(nullptr, PLD_STRATEGY_THRESHOLDED, thresholded ? threshold : 0.0, 0.0, promotion);
+  int gx = (int)((total + 255) / 256);
+  if (gx > ctx->num_sms * 8) gx = ctx->num_sms * 8;
+  ordinal_pairs_kernel<<<gx, 256, 0, st>>>(gt, draws, W, H * W, (long long)n_pairs, total, thresholded ? 1 : 0,
+                                           invert_sign ? 1 : 0, C, pairs_out);
+  PLD_CHECK_LAUNCH();
+  return PLD_OK;
+}
+
+int pld_eval_invert_rankings(pld_ctx* ctx, float* rankings, int64_t n_lists, int K, void* stream) {
+  PLD_REQUIRE(ctx && rankings, "null argument");
+  PLD_CHECK_DEVICE(ctx);
+  PLD_REQUIRE(n_lists >= 0 && K >= 1, "bad shape");
+  if (n_lists == 0) return PLD_OK;
+  const long long total = (long long)n_lists * ((K + 1) / 2);
+  int gx = (int)((total + 255) / 256);
+  if (gx > ctx->num_sms * 8) gx = ctx->num_sms * 8;
+  invert_rankings_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(rankings), (long long)n_lists, K);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

@@ -51,3 +51,41 @@ class DictModelParams(object):
 
     def set_parameter(self, name, value):
         self.parameters[name] = value
+
+
+class ListDataset(object):
+    """Stand-in for the ``tf.data.Dataset`` of ``(image, gt)`` elements the evaluation providers iterate
+    (generic_ranking_provider.py:86,181): a list with ``as_numpy_iterator``; the stub's
+    ``tf.data.experimental.cardinality`` returns its length."""
+
+    def __init__(self, elements):
+        self.elements = list(elements)
+
+    def as_numpy_iterator(self):
+        return iter(self.elements)
+
+    def __len__(self):
+        return len(self.elements)
+
+
+def load_reference_eval_providers():
+    """Return the UNMODIFIED reference module ``pldepth.data.providers.generic_ranking_provider``.
+
+    On top of the sampler's stub it needs ``tf.data.experimental.cardinality`` (generic_ranking_provider.py:83,181)
+    and, for ``generate_rankings``, the alias ``np.int`` that NumPy removed in 1.24 (line 189; the reference pins
+    numpy~=1.19.5) -- the alias is installed on the numpy module, no reference source is touched."""
+    load_reference_sampling()
+    import numpy as np
+    tf = sys.modules["tensorflow"]
+    if getattr(tf, "__pld_stub__", False) and not hasattr(tf, "data"):
+        data = types.ModuleType("tensorflow.data")
+        exp = types.ModuleType("tensorflow.data.experimental")
+        exp.cardinality = lambda ds: len(ds)
+        data.experimental = exp
+        tf.data = data
+        sys.modules["tensorflow.data"] = data
+        sys.modules["tensorflow.data.experimental"] = exp
+    if not hasattr(np, "int"):
+        np.int = int
+    import pldepth.data.providers.generic_ranking_provider as ref_eval  # noqa: E402
+    return ref_eval

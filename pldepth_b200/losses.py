@@ -130,3 +130,70 @@ class NegativeLogLikelihoodLoss(object):
 
 
 MetaBatchListMLELoss = NegativeLogLikelihoodLoss
+
+
+class _FusedStepFunction(torch.autograd.Function):
+    """``FusedPLStep`` as a differentiable op: forward = sampling + gather + loss + dense gradient in the step's
+    kernels; backward hands that gradient (times the incoming scalar) to autograd -- no second pass."""
+
+    @staticmethod
+    def forward(ctx, y_pred, gt, mask, step, holder):
+        B = gt.shape[0]
+        dev = y_pred.device
+        pred = y_pred.detach()
+        out = dict(grad=torch.empty(pred.numel(), dtype=torch.float32, device=dev),   # fresh: survives later steps
+                   loss=torch.empty(1, dtype=torch.float32, device=dev),
+                   loss_sum=torch.empty(1, dtype=torch.float64, device=dev),
+                   n_valid=torch.empty(B, dtype=torch.int32, device=dev),
+                   rankings=(torch.empty((B, step.R, step.K, 2), dtype=torch.float32, device=dev)
+                             if step.emit_rankings else None))
+        step.run(gt, mask, pred, out=out)
+        holder.update(out)
+        ctx.save_for_backward(out["grad"])
+        ctx.pred_shape, ctx.pred_dtype = y_pred.shape, y_pred.dtype
+        return out["loss"].reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (g,) = ctx.saved_tensors
+        return (g.reshape(ctx.pred_shape) * grad_output).to(ctx.pred_dtype), None, None, None, None
+
+
+class SampledHourglassNLL(object):
+    """The reference's training-time pair -- ranking sampler in the tf.data map (hourglass_provider.py:55-62,75-86) +
+    ``HourglassNegativeLogLikelihood`` as the compiled Keras loss (PLDepth.py:129-134) -- as ONE differentiable call
+    on device-resident tensors:
+
+        criterion = SampledHourglassNLL(ranking_size=5, rankings_per_image=100, strategy="information")
+        loss = criterion(gt, mask, y_pred)      # gt [B,H,W], mask [B,Hm,Wm], y_pred [B,H,W,1] | [B,1,H,W] | [B,H,W]
+        loss.backward()                         # the dense PL gradient flows into the decoder
+
+    Every call draws fresh lists (Philox stream ``seed``, one offset per call).  Data-parallel shards pass
+    ``global_batch`` (all images of the step) and ``image_base`` (index of this rank's first image) so the loss and
+    gradient carry the global 1 / (B_global * R) factor and the shards draw disjoint streams; the returned loss is
+    then this shard's share of the mean (sum the shares for reporting).  ``last`` holds the buffers of the latest call
+    (``rankings`` when ``emit_rankings=True``, ``loss_sum``, ``n_valid``)."""
+
+    def __init__(self, ranking_size, rankings_per_image, strategy="purely", seed=0, emit_rankings=False,
+                 global_batch=None, image_base=0, candidate_factor=None, threshold=0.03, equality_penalty=-1000,
+                 promotion="nep50", context=None):
+        from .step import FusedPLStep
+        self.step = FusedPLStep(ranking_size, rankings_per_image, seed=seed, emit_rankings=emit_rankings,
+                                global_batch=global_batch, image_base=image_base, strategy=strategy,
+                                candidate_factor=candidate_factor, threshold=threshold,
+                                equality_penalty=equality_penalty, promotion=promotion, context=context)
+        self.last = {}
+
+    def __call__(self, gt, mask, y_pred):
+        if not isinstance(y_pred, torch.Tensor):
+            y_pred = torch.from_dlpack(y_pred)
+        gt = ops.as_cuda(gt, torch.float32, "gt")
+        if gt.dim() == 4 and gt.shape[-1] == 1:
+            gt = gt[..., 0]
+        if gt.dim() == 4 and gt.shape[1] == 1:
+            gt = gt[:, 0]
+        if y_pred.dim() == 4 and y_pred.shape[1] != 1 and y_pred.shape[-1] != 1:
+            raise ValueError("y_pred must have one channel, got %s" % (tuple(y_pred.shape),))
+        if not y_pred.is_contiguous():
+            y_pred = y_pred.contiguous()
+        return _FusedStepFunction.apply(y_pred, gt.contiguous(), mask, self.step, self.last)

@@ -67,12 +67,13 @@ def main():
     ap.add_argument("--ranking-size", type=int, default=5)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--strategy", default="purely", choices=["purely", "masked", "thresholded", "information"])
     args = ap.parse_args()
     import numpy as np
     import torch.distributed as dist
     from pldepth_b200 import synth
     from pldepth_b200.dist import shard_bounds
-    from pldepth_b200.step import FusedPLStep
+    from pldepth_b200.losses import SampledHourglassNLL
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -92,7 +93,8 @@ def main():
     gt = torch.from_numpy(np.stack([np.roll(base, 13 * b, axis=1) for b in range(B)])).to(dev)
     mask = torch.ones((B, H, W), dtype=torch.float32, device=dev)
     images = torch.randn((B, 3, H, W), device=dev).to(memory_format=torch.channels_last)
-    pl = FusedPLStep(K, R, seed=4, global_batch=args.batch, image_base=lo)
+    criterion = SampledHourglassNLL(K, R, strategy=args.strategy, seed=4, global_batch=args.batch, image_base=lo)
+    pl = criterion.step
 
     def train_step(with_pl):
         opt.zero_grad(set_to_none=True)
@@ -100,14 +102,14 @@ def main():
             pred = model(images)
         pred = pred.float().contiguous()                 # (B,1,H,W) == (B,H,W,1) in memory
         if with_pl:
-            out = pl.run(gt, mask, pred.detach())
-            if world > 1:
-                dist.all_reduce(out["loss_sum"])
-            grad = out["grad"].view_as(pred)
+            loss = criterion(gt, mask, pred)             # sampler + gather + PL loss; backward = its dense gradient
+            loss.backward()
+            losses.append(loss.detach())
         else:
-            grad = torch.full_like(pred, 1e-6)
-        pred.backward(gradient=grad)
+            pred.backward(gradient=torch.full_like(pred, 1e-6))
         opt.step()
+
+    losses = []
 
     def timed(fn, n):
         for _ in range(args.warmup):
@@ -125,9 +127,16 @@ def main():
     t_net = timed(lambda: train_step(False), args.steps)
     pred0 = torch.randn((B, H, W, 1), device=dev)
     t_pl = timed(lambda: pl.run(gt, mask, pred0), max(args.steps, 50))
+    loss_first = torch.stack(losses[:args.warmup]).mean()
+    loss_last = torch.stack(losses[-args.warmup:]).mean()
+    if world > 1:                                        # each rank holds its share of the global mean
+        both = torch.stack([loss_first, loss_last])
+        dist.all_reduce(both)
+        loss_first, loss_last = both[0], both[1]
     if rank == 0:
-        print(json.dumps({"config": "C4 ff_effnet training step, %dx%d, global batch %d over %d GPU(s), K=%d, R=%d"
-                                    % (H, W, args.batch, world, K, R),
+        print(json.dumps({"config": "C4 ff_effnet training step, %dx%d, global batch %d over %d GPU(s), K=%d, R=%d, "
+                                    "sampler %s" % (H, W, args.batch, world, K, R, args.strategy),
+                          "loss_first_steps": float(loss_first), "loss_last_steps": float(loss_last),
                           "train_step_ms": t_full, "network_only_ms": t_net, "pl_path_ms": t_pl,
                           "pl_share_of_step": t_pl / t_full, "lists_per_step": args.batch * R,
                           "images_per_s": args.batch / (t_full * 1e-3)}))

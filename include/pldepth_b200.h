@@ -47,6 +47,7 @@ extern "C" {
 #define PLD_ST_EMPTY_MASK 1   /* an image has no valid mask pixel (reference: randint(0) raises) */
 #define PLD_ST_BAD_INDEX 2    /* a fed flat index / selection is outside its map */
 #define PLD_ST_MT_EXHAUSTED 4 /* the fed MT19937 word stream ended before all draws were accepted */
+#define PLD_ST_INTERNAL 8     /* a self-check of the library failed (never expected; results of the call are void) */
 
 /* strategies of pldepth/data/sampling.py */
 #define PLD_STRATEGY_PURELY 0      /* PurelyMaskedRandomSamplingStrategy, sampling.py:106-150 */

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PLDEPTH_B200_LIB") or os.path.join(_HERE, "libpldepth
 
 PLD_MAX_RANKING_SIZE = 512
 PLD_MAX_PIXELS = 1 << 23
-ST_EMPTY_MASK, ST_BAD_INDEX, ST_MT_EXHAUSTED = 1, 2, 4
+ST_EMPTY_MASK, ST_BAD_INDEX, ST_MT_EXHAUSTED, ST_INTERNAL = 1, 2, 4, 8
 STRATEGY = {"purely": 0, "masked": 1, "thresholded": 2, "information": 3}
 PROMOTION = {"nep50": 0, "legacy": 1}
 
@@ -172,6 +172,8 @@ class Context(object):
             raise IndexError("ranking index outside the prediction map / valid-pixel table")
         if s & ST_MT_EXHAUSTED:
             raise PLDError("MT19937 word stream exhausted")
+        if s & ST_INTERNAL:
+            raise PLDError("internal self-check failed (top-R selection); the results of the call are void")
         return s
 
 

@@ -56,6 +56,36 @@ __device__ __forceinline__ void launch_offset(const ListParams& P, uint32_t& off
   }
 }
 
+// K Philox draws of list l of image (image_base + b), mapped to [0, M)
+template <int K>
+__device__ __forceinline__ void draw_philox(const ListParams& P, uint32_t off_lo, uint32_t off_hi16, int b, int l,
+                                            uint32_t M, uint32_t thresh, int (&sel)[K]) {
+  const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), off_lo, off_hi16, P.seed_lo, P.seed_hi};
+  bool rej = false;
+#pragma unroll
+  for (int q = 0; q < (K + 3) / 4; ++q) {
+    const Philox4 r = ds.block((uint32_t)q);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = q * 4 + j;
+      if (k < K) sel[k] = (int)lemire_try(w[j], M, thresh, rej);
+    }
+  }
+  if (rej) {  // rare (P < K * M / 2^32): redo with the redraw stream
+#pragma unroll
+    for (int q = 0; q < (K + 3) / 4; ++q) {
+      const Philox4 r = ds.block((uint32_t)q);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = q * 4 + j;
+        if (k < K) sel[k] = (int)lemire_bounded(w[j], M, thresh, ds, (uint32_t)k);
+      }
+    }
+  }
+}
+
 // fire-and-forget float add into the dense gradient map (RED, no return value)
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 #ifdef PLD_USE_ATOMG

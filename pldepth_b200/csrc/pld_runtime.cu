@@ -507,6 +507,7 @@ int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
 size_t seg_radix_sort_hist_bytes(int len_max, int B);
 bool select_small_fits(int n);
 int select_small_init();
+int pilot_select_init();
 int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
                  uint32_t* order, int32_t* order_out, cudaStream_t st);
 
@@ -535,6 +536,8 @@ static int ctx_init(pld_ctx* c, int device) {
   int rc = c->ensure_partials(4096);
   if (rc) return rc;
   rc = select_small_init();
+  if (rc) return rc;
+  rc = pilot_select_init();
   if (rc) return rc;
   PLD_CUDA(cudaDeviceSynchronize());
   return PLD_OK;

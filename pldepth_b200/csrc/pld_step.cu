@@ -11,6 +11,8 @@
 // The path is bound by divergent L1TEX sector accesses, not by HBM bytes, which
 // is why spending 16-20 streamed bytes per pixel to save one random sector per draw pays off
 // once an image receives more draws than about two per pixel.
+#include <stdlib.h>
+
 #include "pld_lists.cuh"
 
 namespace pld {
@@ -26,6 +28,10 @@ size_t seg_radix_sort_hist_bytes(int len_max, int B);
 bool select_small_fits(int n);
 int select_small(const uint64_t* keys, const double* scores, int n, size_t stride, int B, int R, bool ascending_ids,
                  uint32_t* order, int32_t* order_out, cudaStream_t st);
+bool pilot_select_fits(int n);
+size_t pilot_select_bytes(int B, int n, int R, int num_sms, size_t* offs);
+int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, int32_t* order_out, int num_sms,
+                 uint32_t** order_dev, cudaStream_t st);
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_ITEMS = 16;
@@ -713,6 +719,53 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const size_t o_counts = take(sizeof(int) * (size_t)B * nchunks);
   const size_t o_nv = take(sizeof(int32_t) * B);
   const size_t o_mm = take(sizeof(float) * 2 * B);
+  // rankings not materialised, many candidates: sampled-window selection (pld_pilot.cu) -- no key array, no histogram
+  // passes; the deterministic mode keeps the order-preserving path below (the window path appends with atomics)
+  const bool pilot = (rankings == nullptr) && !ctx->deterministic && pilot_select_fits(n) && getenv("PLD_NO_PILOT") == nullptr;
+  if (pilot) {
+    size_t poffs[16];
+    const size_t o_pilot = take(pilot_select_bytes(B, n, R, ctx->num_sms, poffs));
+    const size_t o_ptab = take(sizeof(float2) * (size_t)B * tstride);
+    int prc = ctx->ensure_scratch(off);
+    if (prc) return prc;
+    char* psb = (char*)ctx->d_scratch;
+    int* pcounts = (int*)(psb + o_counts);
+    int32_t* pnv = n_valid ? n_valid : (int32_t*)(psb + o_nv);
+    float* pminmax = (float*)(psb + o_mm);
+    float2* ptable = (float2*)(psb + o_ptab);
+    const int pcap = lists_per_image_cap(ctx->num_sms, B);
+    prc = ctx->ensure_partials(pcap * B + B);
+    if (prc) return prc;
+    const size_t pgtotal = (size_t)B * HW;
+    prc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, pcounts, ptable, tstride, pnv, nullptr, nullptr, grad, st);
+    if (prc) return prc;
+    if (strategy == PLD_STRATEGY_INFORMATION) {
+      gt_minmax_step_kernel<<<B, 1024, 0, st>>>(gt, HW, pminmax);
+      PLD_CHECK_LAUNCH();
+    }
+    ListParams P = {};
+    P.gt = gt; P.pred = pred ? pred : gt; P.n_valid = pnv; P.table = ptable; P.table_stride = tstride;
+    P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
+    P.B = B; P.HW = HW; P.n = n; P.K = K; P.scale = scale;
+    P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+    P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
+    P.image_base = image_base;
+    if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
+    P.score_cfg = make_score_cfg(pminmax, strategy, threshold, equality_penalty, promotion);
+    const int plow = (promotion == PLD_PROMOTION_NEP50 && strategy != PLD_STRATEGY_INFORMATION) ? 1 : 0;
+    uint32_t* porder = nullptr;
+    prc = pilot_select(P, R, plow, psb + o_pilot, order_out, ctx->num_sms, &porder, st);
+    if (prc) return prc;
+    P.n = R;
+    P.list_map = porder; P.map_stride = (size_t)R;
+    P.per_list = per_list; P.grad = grad; P.loss = loss; P.loss_sum = loss_sum;
+    ctx->time_begin(st);
+    prc = launch_lists_small(P, SRC_PHILOX_TAB, loss != nullptr, ctx->num_sms, st);
+    ctx->time_end(st);
+    if (prc == PLD_OK && ctx->use_device_offset) prc = launch_offset_advance(ctx, st);
+    (void)pgtotal;
+    return prc;
+  }
   const size_t o_prefix = take(sizeof(uint64_t) * B);
   const size_t o_rem = take(sizeof(int) * B);
   const size_t o_nsurv = take(sizeof(int) * B);

@@ -110,6 +110,6 @@ def test_random_scored_step(cuda_device, seed):
     # unordered selection (rankings not materialised): same kept set
     out3 = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, promotion, seed=seed, offset=3,
                                  want_rankings=False, want_order=True)
-    assert torch.equal(out3["order"], torch.sort(order, dim=1).values)
+    assert torch.equal(torch.sort(out3["order"], dim=1).values, torch.sort(order, dim=1).values)
     assert abs(out3["loss"].item() - want_loss) <= 1e-5 * max(abs(want_loss), 1e-12)
     assert np.abs(out3["grad"].cpu().numpy() - want_grad).max() / np.abs(want_grad).max() <= 1e-5

@@ -298,7 +298,7 @@ def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K,
     out3 = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, promotion, seed=4, offset=2,
                                  image_base=1, want_rankings=False, want_order=True)
     assert out3["rankings"] is None
-    assert torch.equal(out3["order"], torch.sort(order, dim=1).values)
+    assert torch.equal(torch.sort(out3["order"], dim=1).values, torch.sort(order, dim=1).values)
     assert abs(out3["loss"].item() - want_loss) <= 1e-5 * abs(want_loss)
     assert np.abs(out3["grad"].cpu().numpy() - want_grad).max() / np.abs(want_grad).max() <= 1e-5
 
@@ -461,5 +461,58 @@ def test_scored_step_at_config2_scale(cuda_device, strategy):
         assert np.array_equal(order[b].cpu().numpy(), _want_order(sc_h[b], R))
     out3 = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, 0.03, -1000, "nep50", seed=9, offset=1,
                                  want_rankings=False, want_order=True)
-    assert torch.equal(out3["order"], torch.sort(order, dim=1).values)
+    assert torch.equal(torch.sort(out3["order"], dim=1).values, torch.sort(order, dim=1).values)
     assert abs(out3["loss"].item() - out["loss"].item()) <= 1e-6 * abs(out["loss"].item())
+
+
+@pytest.mark.parametrize("strategy,K,n,R,kind", [
+    ("thresholded", 5, 9000, 6000, "smooth"),
+    ("information", 5, 40000, 8000, "smooth"),
+    ("masked", 3, 20000, 19999, "ties"),        # a handful of distinct scores: the boundary bucket is huge
+    ("information", 8, 12000, 1, "smooth"),
+    ("thresholded", 2, 30000, 30000, "ties"),   # R == n: everything is kept
+    ("masked", 16, 10000, 2500, "const"),       # one distinct score: the cut is decided by candidate ids alone
+])
+@pytest.mark.parametrize("z", [None, "0", "0.5"])
+def test_sampled_window_selection_keeps_the_exact_set(cuda_device, strategy, K, n, R, kind, z):
+    """Rankings not materialised and more than 8192 candidates per image: the top-R set comes from the sampled-window
+    selection (pld_pilot.cu).  It must be exactly the set the ordered pipeline keeps -- also when the window misses
+    (PLD_PILOT_Z = 0 / 0.5 shrink it until the exact fallback runs for most images) and for holed masks."""
+    import os
+    from pldepth_b200 import ops, synth
+    B, H, W = 3, 96, 80
+    rs = np.random.RandomState(n + R)
+    if kind == "smooth":
+        gt = np.stack([synth.depth_map(H, W, 70 + b) for b in range(B)])
+    elif kind == "ties":
+        gt = (rs.randint(0, 5, size=(B, H, W)) / 8 + 0.1).astype(np.float32)
+    else:
+        gt = np.full((B, H, W), 0.5, np.float32)
+    mask = np.stack([synth.valid_mask(H, W, 80 + b, 0.15 * b) for b in range(B)])
+    pred = rs.randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    ref = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, seed=21, offset=5, want_order=True)
+    old = os.environ.get("PLD_PILOT_Z")
+    try:
+        if z is not None:
+            os.environ["PLD_PILOT_Z"] = z
+        out = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, seed=21, offset=5, want_rankings=False,
+                                    want_order=True)
+        ops.check_status(cuda_device)
+    finally:
+        if old is None:
+            os.environ.pop("PLD_PILOT_Z", None)
+        else:
+            os.environ["PLD_PILOT_Z"] = old
+    assert torch.equal(torch.sort(out["order"], dim=1).values, torch.sort(ref["order"], dim=1).values)
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+    g, g_ref = out["grad"].cpu().numpy(), ref["grad"].cpu().numpy()
+    assert np.abs(g - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
+    # the order-preserving selection (PLD_NO_PILOT) keeps the same set as well
+    os.environ["PLD_NO_PILOT"] = "1"
+    try:
+        out_old = ops.fused_step_scored(mask_d, gt_d, pred_d, K, n, R, strategy, seed=21, offset=5, want_rankings=False,
+                                        want_order=True)
+    finally:
+        os.environ.pop("PLD_NO_PILOT", None)
+    assert torch.equal(out_old["order"], torch.sort(ref["order"], dim=1).values)

@@ -81,6 +81,9 @@ struct pld_ctx {
   int ensure_acc(size_t elems);
   unsigned long long* d_offset;  // device-resident Philox offset counter (pld_ctx_device_offset)
   int use_device_offset;
+  unsigned int* d_mm_acc;        // [mm_cap, 2] per-image (~ordered min, ordered max) of gt, zero between calls
+  int mm_cap;
+  int ensure_mm(int B);
   int ensure_scratch(size_t bytes);
   int ensure_partials(int n);
   inline void time_begin(cudaStream_t st) { if (ev_cap > 0 && ev_count < ev_cap) cudaEventRecord(ev_start[ev_count], st); }

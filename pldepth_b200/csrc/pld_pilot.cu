@@ -222,8 +222,11 @@ __global__ void __launch_bounds__(1024) pilot_rank_kernel(const PilotParams Q, c
 #ifndef PLD_SCORESEL_MINBLOCKS
 #define PLD_SCORESEL_MINBLOCKS 3
 #endif
+#ifndef PLD_SCORESEL_LPT
+#define PLD_SCORESEL_LPT 1
+#endif
 template <int K>
-__global__ void __launch_bounds__(256, (K <= 8) ? PLD_SCORESEL_MINBLOCKS : 2) score_select_kernel(const ListParams P,
+__global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_MINBLOCKS : 2)) score_select_kernel(const ListParams P,
                                                                                                  const PilotParams Q,
                                                                                                  int only_flagged) {
   __shared__ int s_cnt[2];
@@ -246,40 +249,52 @@ __global__ void __launch_bounds__(256, (K <= 8) ? PLD_SCORESEL_MINBLOCKS : 2) sc
   uint32_t* sv = Q.sure_v + seg;
   uint64_t* bk = Q.band_k + seg;
   uint32_t* bv = Q.band_v + seg;
-  const int stride = gridDim.x * 256;
-  float pre[K];
-  int base = blockIdx.x * 256;
+  constexpr int LPT = PLD_SCORESEL_LPT;     // lists per thread and iteration: LPT * K gathers in flight per thread
+  const int stride = gridDim.x * 256 * LPT;
+  float pre[LPT][K];
+  int base = blockIdx.x * 256 * LPT;
   if (ok && base < n) {
-    const int l = base + threadIdx.x;
-    issue_depths<K>(P, D, off_lo, off_hi16, b, l < n ? l : n - 1, pre);
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+      const int l = base + j * 256 + threadIdx.x;
+      issue_depths<K>(P, D, off_lo, off_hi16, b, l < n ? l : n - 1, pre[j]);
+    }
   }
   for (; ok && base < n; base += stride) {
-    const int l = base + threadIdx.x;
-    const bool active = l < n;
-    float gs[K];
+    float gs[LPT][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) gs[k] = pre[k];
-    if (base + stride < n) {   // next list's draws and gathers go out before this one is scored
-      const int ln = base + stride + threadIdx.x;
-      issue_depths<K>(P, D, off_lo, off_hi16, b, ln < n ? ln : n - 1, pre);
+    for (int j = 0; j < LPT; ++j)
+#pragma unroll
+      for (int k = 0; k < K; ++k) gs[j][k] = pre[j][k];
+    if (base + stride < n) {   // the next lists' draws and gathers go out before these are scored
+#pragma unroll
+      for (int j = 0; j < LPT; ++j) {
+        const int ln = base + stride + j * 256 + threadIdx.x;
+        issue_depths<K>(P, D, off_lo, off_hi16, b, ln < n ? ln : n - 1, pre[j]);
+      }
     }
-    const uint64_t key = candidate_key<K>(gs, P.score_cfg, b);
-    const bool sure = active && key > t_hi;
-    const bool band = active && !sure && key >= t_lo;
-    const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
-    int base_s = 0, base_b = 0;
-    if (lane == 0) {
-      if (ms) base_s = atomicAdd(&s_cnt[0], __popc(ms));
-      if (mb) base_b = atomicAdd(&s_cnt[1], __popc(mb));
-    }
-    base_s = __shfl_sync(0xffffffffu, base_s, 0);
-    base_b = __shfl_sync(0xffffffffu, base_b, 0);
-    if (sure) sv[base_s + __popc(ms & lt)] = (uint32_t)l;
-    if (band) {
-      const int pos = base_b + __popc(mb & lt);
-      bk[pos] = key;
-      bv[pos] = (uint32_t)l;
-      atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+      const int l = base + j * 256 + threadIdx.x;
+      const bool active = l < n;
+      const uint64_t key = candidate_key<K>(gs[j], P.score_cfg, b);
+      const bool sure = active && key > t_hi;
+      const bool band = active && !sure && key >= t_lo;
+      const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
+      int base_s = 0, base_b = 0;
+      if (lane == 0) {
+        if (ms) base_s = atomicAdd(&s_cnt[0], __popc(ms));
+        if (mb) base_b = atomicAdd(&s_cnt[1], __popc(mb));
+      }
+      base_s = __shfl_sync(0xffffffffu, base_s, 0);
+      base_b = __shfl_sync(0xffffffffu, base_b, 0);
+      if (sure) sv[base_s + __popc(ms & lt)] = (uint32_t)l;
+      if (band) {
+        const int pos = base_b + __popc(mb & lt);
+        bk[pos] = key;
+        bv[pos] = (uint32_t)l;
+        atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
+      }
     }
   }
   __syncthreads();
@@ -587,12 +602,13 @@ bool pilot_select_fits(int n) { return n > PILOT_SAMPLE; }
 
 static void pilot_geometry(int B, int n, int num_sms, int* nseg, int* seg_cap) {
   const int per_image_cap = lists_per_image_cap(num_sms, B);
-  int gx = (n + 255) / 256;
+  const int per_cta = 256 * PLD_SCORESEL_LPT;
+  int gx = (n + per_cta - 1) / per_cta;
   if (gx > per_image_cap) gx = per_image_cap;
   if (gx < 1) gx = 1;
-  const int stride = gx * 256;
+  const int stride = gx * per_cta;
   *nseg = gx;
-  *seg_cap = ((n + stride - 1) / stride) * 256;      // lists one CTA of the scoring pass can see
+  *seg_cap = ((n + stride - 1) / stride) * per_cta;      // lists one CTA of the scoring pass can see
 }
 
 constexpr int PILOT_NOFFS = 14;

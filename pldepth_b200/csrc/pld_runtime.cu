@@ -67,6 +67,24 @@ int pld_ctx::ensure_acc(size_t elems) {
   return PLD_OK;
 }
 
+int pld_ctx::ensure_mm(int B) {
+  if (B <= mm_cap) return PLD_OK;
+  if (d_mm_acc) {
+    cudaDeviceSynchronize();
+    cudaFree(d_mm_acc);
+    d_mm_acc = nullptr;
+    mm_cap = 0;
+  }
+  if (cudaMalloc(&d_mm_acc, sizeof(unsigned int) * 2 * (size_t)B) != cudaSuccess ||
+      cudaMemset(d_mm_acc, 0, sizeof(unsigned int) * 2 * (size_t)B) != cudaSuccess) {
+    cudaGetLastError();
+    pld::set_error("min/max accumulator allocation failed");
+    return PLD_ENOMEM;
+  }
+  mm_cap = B;
+  return PLD_OK;
+}
+
 int pld_ctx::ensure_partials(int n) {
   if (n <= partials_cap) return PLD_OK;
   if (d_partials) {
@@ -578,6 +596,7 @@ int pld_ctx_destroy(pld_ctx* ctx) {
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_acc);
+  cudaFree(ctx->d_mm_acc);
   cudaFree(ctx->d_offset);
   pld_ctx_kernel_timing(ctx, 0);
   delete ctx;

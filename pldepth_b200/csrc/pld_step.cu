@@ -93,9 +93,43 @@ template <typename MT>
 __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __restrict__ mask, int Nm, int nchunks,
                                                                int* __restrict__ counts, float4* __restrict__ grad4,
                                                                size_t grad_n4, float* __restrict__ grad_tail,
-                                                               int grad_tail_n) {
+                                                               int grad_tail_n, const float* __restrict__ gt, int HW,
+                                                               unsigned int* __restrict__ mm_acc) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
+  if (mm_acc != nullptr) {
+    // np.amin(gt), np.amax(gt) of the image (sampling.py:219-220; NaNs ignored like fminf / fmaxf): every CTA of the
+    // image reduces a strided share and merges it with two atomics on order-preserving encodings (~min, max; both
+    // start from 0 and are reset by prep_build_kernel once converted)
+    const float* g = gt + (size_t)b * HW;
+    unsigned int omin = 0u, omax = 0u;
+    for (int i0 = chunk * PC_THREADS + threadIdx.x; i0 < HW; i0 += gridDim.x * PC_THREADS * 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * gridDim.x * PC_THREADS;
+        v[j] = i < HW ? __ldg(g + i) : __ldg(g + i0);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (v[j] == v[j]) {
+          const unsigned int o = float_to_ordered(v[j]);
+          omax = o > omax ? o : omax;
+          omin = ~o > omin ? ~o : omin;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned int a = __shfl_xor_sync(0xffffffffu, omin, o), c = __shfl_xor_sync(0xffffffffu, omax, o);
+      omin = a > omin ? a : omin;
+      omax = c > omax ? c : omax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (omin) atomicMax(mm_acc + 2 * b, omin);
+      if (omax) atomicMax(mm_acc + 2 * b + 1, omax);
+    }
+  }
   const MT* m = mask + (size_t)b * Nm;
   const int base = chunk * PC_CHUNK + threadIdx.x * PC_ITEMS;
   const int c = (base < Nm) ? __popc(flags16(m, base, Nm)) : 0;
@@ -114,9 +148,17 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     const MT* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
     int W, int HW, double xs, double ys, int identity_scale, int nchunks, const int* __restrict__ counts,
     float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid, int32_t* __restrict__ vj_flat,
-    float* __restrict__ grad_valid) {
+    float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc, float* __restrict__ minmax) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
+  if (mm_acc != nullptr && chunk == 0 && threadIdx.x == 0) {
+    // min / max of gt collected by prep_count_kernel -> floats for the scoring passes; accumulators back to zero
+    const unsigned int omin = ~mm_acc[2 * b], omax = mm_acc[2 * b + 1];
+    minmax[2 * b] = mm_acc[2 * b] ? ordered_to_float(omin) : 3.402823466e38f;
+    minmax[2 * b + 1] = mm_acc[2 * b + 1] ? ordered_to_float(omax) : -3.402823466e38f;
+    mm_acc[2 * b] = 0u;
+    mm_acc[2 * b + 1] = 0u;
+  }
   int pre = 0, all = 0;
   for (int i = threadIdx.x; i < nchunks; i += PC_THREADS) {
     const int c = counts[b * nchunks + i];
@@ -217,36 +259,6 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
 // is compacted in candidate order and fully sorted afterwards.
 // ------------------------------------------------------------------------------------------
 constexpr int SEL_BINS = 4096;
-
-// np.amin(gt), np.amax(gt) of every image (sampling.py:219-220): one 1024-thread CTA per image, eight loads in flight
-// per thread (a 256-thread scalar loop took 34 us for 32 images of 448 x 448)
-__global__ void __launch_bounds__(1024) gt_minmax_step_kernel(const float* __restrict__ gt, int HW, float* __restrict__ out) {
-  const float* g = gt + (size_t)blockIdx.x * HW;
-  float mn = 3.402823466e38f, mx = -3.402823466e38f;
-  for (int i0 = threadIdx.x; i0 < HW; i0 += 8 * 1024) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + j * 1024;
-      v[j] = (i < HW) ? __ldg(g + i) : __ldg(g + threadIdx.x % HW);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  __shared__ float smn[32], smx[32];
-  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 32; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
-    out[blockIdx.x * 2 + 0] = mn;
-    out[blockIdx.x * 2 + 1] = mx;
-  }
-}
 
 __global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B,
                                                        unsigned long long* bits_or, unsigned long long* bits_and,
@@ -574,7 +586,7 @@ using namespace pld;
 template <typename MT>
 static int launch_prep(const MT* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
                        int* counts, float2* table, size_t tstride, int32_t* nv, int32_t* vj_flat, float* grad_valid,
-                       float* grad, cudaStream_t st) {
+                       float* grad, cudaStream_t st, unsigned int* mm_acc = nullptr, float* minmax = nullptr) {
   const int HW = H * W, Nm = Hm * Wm;
   const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
   dim3 grid((unsigned)nchunks, (unsigned)B);
@@ -588,12 +600,13 @@ static int launch_prep(const MT* mask, const float* gt, const float* pred, int B
     n4 = gtotal / 4;
     tail = (int)(gtotal - n4 * 4);
   }
-  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail);
+  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail,
+                                                     gt, HW, mm_acc);
   PLD_CHECK_LAUNCH();
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
   prep_build_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv, vj_flat, grad_valid);
+                                                table, tstride, nv, vj_flat, grad_valid, mm_acc, minmax);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
@@ -737,12 +750,15 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     prc = ctx->ensure_partials(pcap * B + B);
     if (prc) return prc;
     const size_t pgtotal = (size_t)B * HW;
-    prc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, pcounts, ptable, tstride, pnv, nullptr, nullptr, grad, st);
-    if (prc) return prc;
+    unsigned int* pmm = nullptr;
     if (strategy == PLD_STRATEGY_INFORMATION) {
-      gt_minmax_step_kernel<<<B, 1024, 0, st>>>(gt, HW, pminmax);
-      PLD_CHECK_LAUNCH();
+      prc = ctx->ensure_mm(B);
+      if (prc) return prc;
+      pmm = ctx->d_mm_acc;
     }
+    prc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, pcounts, ptable, tstride, pnv, nullptr, nullptr, grad, st,
+                      pmm, pminmax);
+    if (prc) return prc;
     ListParams P = {};
     P.gt = gt; P.pred = pred ? pred : gt; P.n_valid = pnv; P.table = ptable; P.table_stride = tstride;
     P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
@@ -809,12 +825,15 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
 
   // 1. valid pixels + zeroed grad + lookup tables (as pld_fused_step)
   const size_t gtotal = (size_t)B * HW;
-  rc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, counts, table, tstride, nv, nullptr, nullptr, grad, st);
-  if (rc) return rc;
+  unsigned int* mm_acc = nullptr;
   if (strategy == PLD_STRATEGY_INFORMATION) {
-    gt_minmax_step_kernel<<<B, 1024, 0, st>>>(gt, HW, minmax);
-    PLD_CHECK_LAUNCH();
+    rc = ctx->ensure_mm(B);
+    if (rc) return rc;
+    mm_acc = ctx->d_mm_acc;
   }
+  rc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, counts, table, tstride, nv, nullptr, nullptr, grad, st, mm_acc,
+                   minmax);
+  if (rc) return rc;
 
   // 2. scoring pass over the n candidates of every image: ordered scores only
   ListParams P = {};

@@ -226,9 +226,15 @@ int pld_fused_step_m8(pld_ctx* ctx, const uint8_t* mask, const float* gt, const 
  * selection + segmented radix sort above that -- and the kept lists are
  * REDRAWN from their Philox list ids inside the fused kernel that emits rankings / loss / gradient.
  * Results equal pld_sample_lists_philox(n) -> pld_score_lists -> pld_select_top(R) -> pld_listmle_fwd_bwd.
- * pred / loss / grad may be NULL (sampler only: rankings and order_out).  ranking_size 1..16.
+ * pred / loss / grad may be NULL (sampler only: rankings and order_out).  ranking_size 1..512: thread-per-list
+ * kernels up to 16, above that the group-per-list kernel scores the ordered depths (per-position terms in parallel,
+ * NumPy's pairwise / sequential summation order by one lane of the group).
  * With rankings == NULL nobody observes the order of the kept lists (the loss is invariant to it): the sort is
- * replaced by an exact radix selection and order_out lists the kept candidates in ascending candidate order.
+ * replaced by an exact selection of the same SET and order_out lists the kept candidates in unspecified order.
+ * Above 8192 candidates per image that selection is the sampled-window one (csrc/pld_pilot.cu: thresholds from the
+ * first 8192 candidates, which are an i.i.d. sample; the scoring pass stores only candidates above / inside the
+ * window; exact cut inside it; exact fallback over all candidates whenever a window misses).  In deterministic mode
+ * (pld_ctx_set_deterministic) the order-preserving radix selection is used instead (ascending candidate order).
  *   -> order_out i32[B,R] (nullable): candidate index of every kept list */
 int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const float* gt, const float* pred, int B, int Hm,
                           int Wm, int H, int W, int K, int n, int R, int strategy, double threshold,

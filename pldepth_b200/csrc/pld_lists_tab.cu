@@ -108,7 +108,9 @@ __device__ __noinline__ void exact_order(const float2* own, bool gs_layout, uint
 #define PLD_TAB_MINBLOCKS 3
 #endif
 
-template <int LPL, int IPL, int THREADS, bool LOSS>
+// SCORE: scoring pass of the score-based strategies -- the ordered depths of every candidate list are turned into its
+// 8-byte score key (NumPy-exact arithmetic, pld_score.cuh) and nothing else leaves the kernel.
+template <int LPL, int IPL, int THREADS, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS : 4) lists_tab_kernel(const ListParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // Parking buffers.  A lane owns ROW = IPL + 1 consecutive entries (the odd stride keeps its own 8-byte accesses at the
@@ -279,6 +281,59 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS 
       if (GS) { lab[i] = e2[i].x; sv[i] = e2[i].y; p[i] = (int)ax[i]; }
       else { lab[i] = e2[i].y; sv[i] = __uint_as_float(ax[i]); p[i] = __float_as_int(e2[i].x); }
     }
+    if constexpr (SCORE) {
+      // Per-position parts in parallel (lane gl owns sorted positions gl*IPL + i): chi term or |difference| into the
+      // lane's own parking row, "equal relation with the next position" into its aux row; then lane 0 of the group
+      // combines them serially in NumPy's order of operations (score_combine) -- the same code the staged
+      // pld_score_lists runs, so both pipelines produce identical keys.
+      const ScoreCfg& C = P.score_cfg;
+      const bool info = C.strategy == PLD_STRATEGY_INFORMATION;
+      const bool want_eq = info || C.strategy == PLD_STRATEGY_THRESHOLDED;
+      const float nxt0 = __shfl_down_sync(0xffffffffu, lab[0], 1, LPL);
+      __syncwarp();     // every lane has fetched its payloads: the rows are free
+      auto parts = [&](auto tag) {
+        using T = decltype(tag);
+        T start = (T)0, stop = (T)0, delta = (T)0, step = (T)0;
+        if (info) ladder_setup<T>(C, b, K, start, stop, delta, step);
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) {
+          if (i < nreal) {
+            const int ppos = gl * IPL + i;
+            const float gn = (i + 1 < IPL) ? lab[(i + 1 < IPL) ? i + 1 : i] : nxt0;
+            const bool has_next = ppos + 1 < K;
+            const bool e = (want_eq && has_next) ? relation_equal<T>(lab[i], gn, C) : false;
+            aux[own + i] = e ? 1u : 0u;
+            if (info) {
+              const T c = chi_term<T>(lab[i], ppos, K, start, stop, delta, step);
+              if (sizeof(T) == 4) s_ent[own + i] = make_float2((float)c, 0.f);
+              else *reinterpret_cast<double*>(&s_ent[own + i]) = (double)c;
+            } else {
+              s_ent[own + i] = make_float2(has_next ? fabsf(__fsub_rn(lab[i], gn)) : 0.f, 0.f);
+            }
+          }
+        }
+      };
+      if (C.promotion == PLD_PROMOTION_NEP50) parts(0.f);
+      else parts(0.0);
+      __syncwarp();
+      if (gl == 0) {
+        auto posf = [&](int q) { return grp + q + (q >> LOG_IPL); };
+        auto eqf = [&](int j) { return aux[posf(j)] != 0u; };
+        auto difff = [&](int j) { return s_ent[posf(j)].x; };
+        double sc;
+        if (C.promotion == PLD_PROMOTION_NEP50) {
+          auto chif = [&](int k) { return s_ent[posf(k)].x; };
+          sc = score_combine<float>(chif, difff, eqf, K, C);
+        } else {
+          auto chif = [&](int k) { return *reinterpret_cast<const double*>(&s_ent[posf(k)]); };
+          sc = score_combine<double>(chif, difff, eqf, K, C);
+        }
+        const bool f32_exact = C.promotion == PLD_PROMOTION_NEP50 && !info;
+        if (active) P.score_keys[list_id] = f32_exact ? score_key_f32((float)sc) : score_key(sc);
+      }
+      __syncwarp();   // the combination is done before the rows are refilled
+      return;
+    }
     if (P.rank_out != nullptr && active) {
       float2* ro = reinterpret_cast<float2*>(P.rank_out) + list_id * K + gl * IPL;
       if ((K & 1) == 0) {  // 16-byte stores: list rows are 16-byte aligned when K is even
@@ -346,19 +401,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS 
 }
 
 template <int LPL, int IPL, int THREADS>
-static int launch_tab_cfg(const ListParams& P, bool loss, int num_sms, cudaStream_t st) {
+static int launch_tab_cfg(const ListParams& P, bool loss, int num_sms, cudaStream_t st, bool score = false) {
   constexpr size_t SMEM = (size_t)(IPL + 1) * THREADS * (sizeof(float2) + 2 * sizeof(uint32_t));
-  static bool configured[2] = {false, false};
-  if (!configured[loss ? 1 : 0]) {
-    cudaError_t e = loss ? cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)
-                         : cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  static bool configured[3] = {false, false, false};
+  const int which = score ? 2 : (loss ? 1 : 0);
+  if (!configured[which]) {
+    cudaError_t e = score ? cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, false, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)
+                    : loss ? cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)
+                           : cudaFuncSetAttribute(lists_tab_kernel<LPL, IPL, THREADS, false>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(lists_tab_kernel) failed: %s", cudaGetErrorString(e));
       return PLD_ECUDA;
     }
-    configured[loss ? 1 : 0] = true;
+    configured[which] = true;
   }
   constexpr int GPB = THREADS / LPL;
   const int per_image_cap = lists_per_image_cap(num_sms, P.B);
@@ -368,22 +426,30 @@ static int launch_tab_cfg(const ListParams& P, bool loss, int num_sms, cudaStrea
   dim3 grid((unsigned)gx, (unsigned)P.B);
   ListParams Q = P;
   philox_round_keys(P.seed_lo, P.seed_hi, Q.rk0, Q.rk1);
-  if (loss) lists_tab_kernel<LPL, IPL, THREADS, true><<<grid, THREADS, SMEM, st>>>(Q);
+  if (score) lists_tab_kernel<LPL, IPL, THREADS, false, true><<<grid, THREADS, SMEM, st>>>(Q);
+  else if (loss) lists_tab_kernel<LPL, IPL, THREADS, true><<<grid, THREADS, SMEM, st>>>(Q);
   else lists_tab_kernel<LPL, IPL, THREADS, false><<<grid, THREADS, SMEM, st>>>(Q);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
 
 // SRC_PHILOX_TAB for 17 <= K <= 512
-int launch_lists_tab(const ListParams& P, bool loss, int num_sms, cudaStream_t st) {
+static int launch_tab_any(const ListParams& P, bool loss, bool score, int num_sms, cudaStream_t st) {
   const int K = P.K;
-  if (K <= 32) return launch_tab_cfg<4, 8, 256>(P, loss, num_sms, st);
-  if (K <= 64) return launch_tab_cfg<8, 8, 256>(P, loss, num_sms, st);
-  if (K <= 128) return launch_tab_cfg<16, 8, 256>(P, loss, num_sms, st);
-  if (K <= 256) return launch_tab_cfg<32, 8, 256>(P, loss, num_sms, st);
-  if (K <= 512) return launch_tab_cfg<32, 16, 128>(P, loss, num_sms, st);
+  if (K <= 32) return launch_tab_cfg<4, 8, 256>(P, loss, num_sms, st, score);
+  if (K <= 64) return launch_tab_cfg<8, 8, 256>(P, loss, num_sms, st, score);
+  if (K <= 128) return launch_tab_cfg<16, 8, 256>(P, loss, num_sms, st, score);
+  if (K <= 256) return launch_tab_cfg<32, 8, 256>(P, loss, num_sms, st, score);
+  if (K <= 512) return launch_tab_cfg<32, 16, 128>(P, loss, num_sms, st, score);
   set_error("lists_tab: K=%d out of range", K);
   return PLD_EINVAL;
+}
+int launch_lists_tab(const ListParams& P, bool loss, int num_sms, cudaStream_t st) {
+  return launch_tab_any(P, loss, false, num_sms, st);
+}
+// scoring pass (P.score_keys, P.score_cfg) of the score-based strategies for 17 <= K <= 512
+int launch_lists_tab_score(const ListParams& P, int num_sms, cudaStream_t st) {
+  return launch_tab_any(P, false, true, num_sms, st);
 }
 
 }  // namespace pld

@@ -103,40 +103,46 @@ __device__ T np_pairwise_sum(const F& f, int lo, int n) {
   return A::add(a, b);
 }
 
-// Score of a list whose depths are read through `g(k)` (runtime K).
-template <typename T, typename G>
-__device__ __forceinline__ double score_list(const G& g, int K, const ScoreCfg& C, int b) {
+// Combination step of a list score from its per-position parts (runtime K), in NumPy's order of operations:
+//   chi(k)  = (g_k - e_k)^2 / e_k            (information, type T)        -- see chi_term
+//   diff(j) = |g_j - g_{j+1}|                (masked / thresholded, float32)
+//   eq(j)   = get_depth_relation(g_j, g_{j+1}) == 0
+template <typename T, typename FC, typename FD, typename FE>
+__device__ __forceinline__ double score_combine(const FC& chi, const FD& diff, const FE& eq, int K, const ScoreCfg& C) {
   double score;
   if (C.strategy == PLD_STRATEGY_INFORMATION) {
-    T start, stop, delta, step;
-    ladder_setup<T>(C, b, K, start, stop, delta, step);
-    auto chi = [&](int k) {
-      const T e = ladder<T>(k, K, start, stop, delta, step);
-      const T d = Arith<T>::sub((T)g(k), e);
-      return Arith<T>::div(Arith<T>::mul(d, d), e);
-    };
     const T sum = np_pairwise_sum<T>(chi, 0, K);
     score = (double)(-sum);
-    float gprev = g(0);
-    for (int j = 0; j + 1 < K; ++j) {
-      const float gn = g(j + 1);
-      if (relation_equal<T>(gprev, gn, C)) score = __dadd_rn(score, C.penalty);
-      gprev = gn;
-    }
+    for (int j = 0; j + 1 < K; ++j)
+      if (eq(j)) score = __dadd_rn(score, C.penalty);
   } else {
     T acc = (T)0;
     const T pen = (T)C.penalty;
-    float gprev = g(0);
     for (int j = 0; j + 1 < K; ++j) {
-      const float gn = g(j + 1);
-      const float diff = fabsf(__fsub_rn(gprev, gn));
-      if (C.strategy == PLD_STRATEGY_THRESHOLDED && relation_equal<T>(gprev, gn, C)) acc = Arith<T>::add(acc, pen);
-      acc = Arith<T>::add(acc, (T)diff);
-      gprev = gn;
+      if (C.strategy == PLD_STRATEGY_THRESHOLDED && eq(j)) acc = Arith<T>::add(acc, pen);
+      acc = Arith<T>::add(acc, (T)diff(j));
     }
     score = (double)acc;
   }
   return score;
+}
+
+template <typename T>
+__device__ __forceinline__ T chi_term(float g, int k, int K, T start, T stop, T delta, T step) {
+  const T e = ladder<T>(k, K, start, stop, delta, step);
+  const T d = Arith<T>::sub((T)g, e);
+  return Arith<T>::div(Arith<T>::mul(d, d), e);
+}
+
+// Score of a list whose depths are read through `g(k)` (runtime K).
+template <typename T, typename G>
+__device__ __forceinline__ double score_list(const G& g, int K, const ScoreCfg& C, int b) {
+  T start = (T)0, stop = (T)0, delta = (T)0, step = (T)0;
+  if (C.strategy == PLD_STRATEGY_INFORMATION) ladder_setup<T>(C, b, K, start, stop, delta, step);
+  auto chi = [&](int k) { return chi_term<T>(g(k), k, K, start, stop, delta, step); };
+  auto diff = [&](int j) { return fabsf(__fsub_rn(g(j), g(j + 1))); };
+  auto eq = [&](int j) { return relation_equal<T>(g(j), g(j + 1), C); };
+  return score_combine<T>(chi, diff, eq, K, C);
 }
 
 // Same arithmetic for a list held in registers (compile-time K <= 16, fully unrolled).

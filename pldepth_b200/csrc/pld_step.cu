@@ -21,6 +21,7 @@ int launch_lists_large(const ListParams& P, int src, bool loss, int num_sms, cud
 int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int accumulate, cudaStream_t st);
 int launch_offset_advance(pld_ctx* ctx, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
+int launch_lists_tab_score(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
                    const unsigned long long* varying, int first_pass, cudaStream_t st);
@@ -714,7 +715,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   PLD_REQUIRE(rankings != nullptr || loss != nullptr, "no output requested");
   PLD_REQUIRE(B > 0 && B <= 65535 && Hm > 0 && Wm > 0 && H > 0 && W > 0, "bad shape");
   PLD_REQUIRE((long long)H * W <= PLD_MAX_PIXELS && (long long)Hm * Wm <= PLD_MAX_PIXELS, "map too large");
-  PLD_REQUIRE(K >= 1 && K <= 16, "pld_fused_step_scored supports ranking_size 1..16 (use the staged calls above that)");
+  PLD_REQUIRE(K >= 1 && K <= PLD_MAX_RANKING_SIZE, "ranking_size must be in [1, 512]");
   PLD_REQUIRE(n >= 1 && R >= 1 && R <= n && (long long)B * n < (1ll << 31), "need 1 <= R <= n candidates");
   PLD_REQUIRE(strategy >= PLD_STRATEGY_MASKED && strategy <= PLD_STRATEGY_INFORMATION, "bad strategy");
   PLD_REQUIRE(promotion == PLD_PROMOTION_NEP50 || promotion == PLD_PROMOTION_LEGACY, "bad promotion");
@@ -734,7 +735,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const size_t o_mm = take(sizeof(float) * 2 * B);
   // rankings not materialised, many candidates: sampled-window selection (pld_pilot.cu) -- no key array, no histogram
   // passes; the deterministic mode keeps the order-preserving path below (the window path appends with atomics)
-  const bool pilot = (rankings == nullptr) && !ctx->deterministic && pilot_select_fits(n) && getenv("PLD_NO_PILOT") == nullptr;
+  const bool pilot = (rankings == nullptr) && !ctx->deterministic && K <= 16 && pilot_select_fits(n) &&
+                     getenv("PLD_NO_PILOT") == nullptr;
   if (pilot) {
     size_t poffs[16];
     const size_t o_pilot = take(pilot_select_bytes(B, n, R, ctx->num_sms, poffs));
@@ -847,13 +849,13 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   P.score_keys = keys;
   P.score_cfg = make_score_cfg(minmax, strategy, threshold, equality_penalty, promotion);
   const bool radix_select = !select_small_fits(n);
+  const bool fused_hist = K <= 16;     // the thread-per-list scoring kernel takes the first histogram of the selection
   if (radix_select) {
-    // the scoring pass also takes the first histogram of the selection (top 12 key bits)
     sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and, iprefix);
     PLD_CHECK_LAUNCH();
-    P.sel_hist = shist;
+    if (fused_hist) P.sel_hist = shist;
   }
-  rc = launch_lists_small_score(P, ctx->num_sms, st);
+  rc = (K <= 16) ? launch_lists_small_score(P, ctx->num_sms, st) : launch_lists_tab_score(P, ctx->num_sms, st);
   if (rc) return rc;
   P.sel_hist = nullptr;
 
@@ -866,7 +868,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   int gsel = (n + 255) / 256;
   if (gsel > per_image_cap) gsel = per_image_cap;
   for (int pass = 0; pass < 3; ++pass) {
-    if (pass > 0) {   // pass 0 was histogrammed by the scoring kernel
+    if (pass > 0 || !fused_hist) {   // pass 0 was histogrammed by the thread-per-list scoring kernel
       sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
       PLD_CHECK_LAUNCH();
     }
@@ -925,7 +927,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     PLD_CUDA(cudaMemsetAsync(P.acc, 0, sizeof(long long) * gtotal, st));
   }
   ctx->time_begin(st);
-  rc = launch_lists_small(P, SRC_PHILOX_TAB, do_loss, ctx->num_sms, st);
+  rc = (K <= 16) ? launch_lists_small(P, SRC_PHILOX_TAB, do_loss, ctx->num_sms, st)
+                 : launch_lists_large(P, SRC_PHILOX_TAB, do_loss, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);
   if (rc == PLD_OK && ctx->use_device_offset) rc = launch_offset_advance(ctx, st);

@@ -262,7 +262,8 @@ def fused_step_scored(mask, gt, pred, K, n, R, strategy, threshold=0.03, equalit
                       seed=0, offset=0, image_base=0, scale=None, want_rankings=True, want_grad=True, want_order=False,
                       want_per_list=False):
     """pld_fused_step_scored: draw n candidates/image, score, keep the best R, (optionally) loss + gradient.
-    ``pred`` may be None (sampler only).  Returns dict(loss, loss_sum, grad, rankings, order, per_list, n_valid)."""
+    ``pred`` may be None (sampler only).  ranking_size 1..512 (thread-per-list kernels up to 16, group-per-list above).
+    Returns dict(loss, loss_sum, grad, rankings, order, per_list, n_valid)."""
     mask = as_cuda(mask, torch.float32, "mask")
     gt3 = as_cuda(gt, torch.float32, "gt")
     if gt3.dim() == 4:

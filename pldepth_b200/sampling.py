@@ -173,7 +173,7 @@ class PurelyMaskedRandomSamplingStrategy(RandomSamplingStrategy):
         f = self._default_factor if batch_size_factor is None else batch_size_factor
         n = int(batch_size * f)
         K = int(self._num_points_per_sample)
-        if self.rng == "philox" and self._strategy != "purely" and K <= 16 and n >= 1:
+        if self.rng == "philox" and self._strategy != "purely" and n >= 1:
             # fast path: score-only pass, radix top-R, kept lists redrawn from their Philox ids
             gt3 = ops.as_cuda(gt, torch.float32, "gt")
             if gt3.dim() == 4 and gt3.shape[-1] == 1:

@@ -4,8 +4,8 @@ ListMLE forward + backward, for a batch of images resident on one GPU.
 This is what replaces, per training step, the reference's tf.data sampler map
 (hourglass_provider.py:55-62), ``prepare_fully_fledged_loss_input`` (depth_utils.py:39-61) and the
 TF-Ranking ListMLE loss + its autodiff (nll_loss.py:32-62).  Output buffers are preallocated and
-reused, so a step is three kernel launches on the current stream (ranking_size <= 16; two launches +
-memset + list kernel above that), no host sync.
+reused, so a step is three kernel launches on the current stream (core sampler; the score-based strategies add
+their scoring pass and top-R selection), no host sync.
 """
 import ctypes
 
@@ -123,24 +123,6 @@ class FusedPLStep(object):
         gb = self.global_batch if self.global_batch else B
         scale = 1.0 / (float(gb) * float(self.R))
         p = lambda t: c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
-        if self.strategy != "purely" and self.K > 16:
-            # long lists: the scoring pass of the fused kernel is register-resident (K <= 16); above that the
-            # staged calls do the same work (candidates are materialised once)
-            vf, nv = ops.mask_compact(mask, H, W, ctx=ctx)
-            cand, _ = ops.sample_lists_philox(gt, vf, nv, self.K, self.n_candidates, self.seed, self.step_index,
-                                              self.image_base, ctx=ctx)
-            mm = ops.gt_minmax(gt, ctx=ctx) if self.strategy == "information" else None
-            scores = ops.score_lists(cand, self.strategy, self.threshold, self.equality_penalty, self.promotion, mm,
-                                     ctx=ctx)
-            top, _ = ops.select_top(scores, cand, self.R, ctx=ctx)
-            loss, loss_sum, grad, _ = ops.listmle_fwd_bwd(top, pred, B, self.K, scale, grad_out=buf["grad"], ctx=ctx)
-            buf["loss"].copy_(loss)
-            buf["loss_sum"].copy_(loss_sum)
-            buf["n_valid"].copy_(nv)
-            if buf["rankings"] is not None:
-                buf["rankings"].copy_(top)
-            self.step_index += 1
-            return buf
         if self.strategy != "purely":
             from ._lib import STRATEGY, PROMOTION
             check(lib.pld_fused_step_scored(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K,

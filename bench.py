@@ -369,11 +369,13 @@ class Measurement(object):
         self.barrier()
         e0.record()
         self.fork_lanes(e0)
+        h0 = time.perf_counter()
         for i in range(steps):
             if graphs is not None:
                 graphs[i % self.n_sets].replay()
             else:
                 self.one_step(i)
+        self.host_enqueue_ms = 1e3 * (time.perf_counter() - h0) / max(steps, 1)   # host time to enqueue one step
         self.drain()
         self.join_lanes()
         e1.record()
@@ -508,6 +510,11 @@ def run_b200(args):
     red0 = m.reductions
     sampler.rows.clear()
     ms_total = m.timed(args.steps, graphs)
+    host_enqueue_ms = m.host_enqueue_ms
+    if world > 1:     # slowest host, like the device time
+        t = torch.tensor([host_enqueue_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        host_enqueue_ms = float(t.item())
     launches = _lib.launch_count() - launches0
     reductions = m.reductions - red0
     if graphs is not None:
@@ -615,6 +622,7 @@ def run_b200(args):
                        "cache": "rotating %d input/output buffer sets of %.0f MB each (> 126 MB L2), no reuse "
                                 "between consecutive steps" % (n_sets, roof["algorithmic_bytes"] / 1e6),
                        "cuda_graph": bool(graphs),
+                       "host_enqueue_ms_per_step": host_enqueue_ms,
                        "lanes": "%d independent batches in flight on separate streams (own lookup tables each); "
                                 "roofline.kernel_ms is timed in a separate sequential pass" % n_lanes,
                        "collective": "loss sums all-reduced once per %d steps per lane (LossWindow), %d all-reduce(s) "

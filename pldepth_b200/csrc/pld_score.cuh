@@ -22,7 +22,8 @@ template <> struct Arith<double> {
 };
 
 struct ScoreCfg {
-  const float* gt_minmax;          // [B, 2] (information)
+  const float* gt_minmax;          // [B, 2] (information): min, max of gt -- or, when null,
+  const unsigned int* gt_minmax_enc;  // [B, 2] (~ordered(min), ordered(max)) as collected by prep_build_kernel
   int strategy;                    // PLD_STRATEGY_*
   int promotion;                   // PLD_PROMOTION_*
   double thr_hi, thr_lo, penalty;  // legacy (float64) thresholds
@@ -32,6 +33,7 @@ struct ScoreCfg {
 inline ScoreCfg make_score_cfg(const float* gt_minmax, int strategy, double threshold, double penalty, int promotion) {
   ScoreCfg c;
   c.gt_minmax = gt_minmax;
+  c.gt_minmax_enc = nullptr;
   c.strategy = strategy;
   c.promotion = promotion;
   c.thr_hi = 1.0 + threshold;          // depth_utils.py:16
@@ -64,9 +66,12 @@ __device__ __forceinline__ T ladder(int k, int K, T start, T stop, T delta, T st
 
 template <typename T>
 __device__ __forceinline__ void ladder_setup(const ScoreCfg& C, int b, int K, T& start, T& stop, T& delta, T& step) {
-  if (sizeof(T) == 4) start = (T)__fadd_rn(C.gt_minmax[b * 2], 0.001f);      // sampling.py:223
-  else start = (T)__dadd_rn((double)C.gt_minmax[b * 2], 0.001);
-  stop = (T)C.gt_minmax[b * 2 + 1];
+  float mn, mx;
+  if (C.gt_minmax != nullptr) { mn = C.gt_minmax[b * 2]; mx = C.gt_minmax[b * 2 + 1]; }
+  else { mn = ordered_to_float(~C.gt_minmax_enc[b * 2]); mx = ordered_to_float(C.gt_minmax_enc[b * 2 + 1]); }
+  if (sizeof(T) == 4) start = (T)__fadd_rn(mn, 0.001f);      // sampling.py:223
+  else start = (T)__dadd_rn((double)mn, 0.001);
+  stop = (T)mx;
   delta = Arith<T>::sub(stop, start);
   step = Arith<T>::div(delta, (T)K);
 }

@@ -90,47 +90,42 @@ __device__ __forceinline__ int block_sum_int(int v, int* s_warp) {
   return t;
 }
 
+// np.amin(gt), np.amax(gt) of an image (sampling.py:219-220; NaNs ignored like fminf / fmaxf) on order-preserving
+// encodings, both accumulated with atomicMax from zero: slot 0 = ~ordered(min), slot 1 = ordered(max)
+struct MinMaxAcc {
+  unsigned int omin = 0u, omax = 0u;
+  __device__ __forceinline__ void add(float v) {
+    if (v == v) {
+      const unsigned int o = float_to_ordered(v);
+      omax = o > omax ? o : omax;
+      omin = ~o > omin ? ~o : omin;
+    }
+  }
+  // CTA-wide (every thread of the CTA calls it): one pair of global atomics per CTA
+  __device__ __forceinline__ void flush(unsigned int* acc) {
+    __shared__ unsigned int s_mm[2];
+    if (threadIdx.x < 2) s_mm[threadIdx.x] = 0u;
+    __syncthreads();
+    omin = __reduce_max_sync(0xffffffffu, omin);
+    omax = __reduce_max_sync(0xffffffffu, omax);
+    if ((threadIdx.x & 31) == 0) {
+      if (omin) atomicMax(&s_mm[0], omin);
+      if (omax) atomicMax(&s_mm[1], omax);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_mm[threadIdx.x]) atomicMax(acc + threadIdx.x, s_mm[threadIdx.x]);
+  }
+};
+
 template <typename MT>
 __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __restrict__ mask, int Nm, int nchunks,
                                                                int* __restrict__ counts, float4* __restrict__ grad4,
                                                                size_t grad_n4, float* __restrict__ grad_tail,
-                                                               int grad_tail_n, const float* __restrict__ gt, int HW,
-                                                               unsigned int* __restrict__ mm_acc) {
+                                                               int grad_tail_n, unsigned int* __restrict__ mm_acc) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
-  if (mm_acc != nullptr) {
-    // np.amin(gt), np.amax(gt) of the image (sampling.py:219-220; NaNs ignored like fminf / fmaxf): every CTA of the
-    // image reduces a strided share and merges it with two atomics on order-preserving encodings (~min, max; both
-    // start from 0 and are reset by prep_build_kernel once converted)
-    const float* g = gt + (size_t)b * HW;
-    unsigned int omin = 0u, omax = 0u;
-    for (int i0 = chunk * PC_THREADS + threadIdx.x; i0 < HW; i0 += gridDim.x * PC_THREADS * 4) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * gridDim.x * PC_THREADS;
-        v[j] = i < HW ? __ldg(g + i) : __ldg(g + i0);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (v[j] == v[j]) {
-          const unsigned int o = float_to_ordered(v[j]);
-          omax = o > omax ? o : omax;
-          omin = ~o > omin ? ~o : omin;
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned int a = __shfl_xor_sync(0xffffffffu, omin, o), c = __shfl_xor_sync(0xffffffffu, omax, o);
-      omin = a > omin ? a : omin;
-      omax = c > omax ? c : omax;
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (omin) atomicMax(mm_acc + 2 * b, omin);
-      if (omax) atomicMax(mm_acc + 2 * b + 1, omax);
-    }
-  }
+  // min / max accumulators of gt (collected by prep_build_kernel, information strategy) start every call from zero
+  if (mm_acc != nullptr && chunk == 0 && threadIdx.x < 2) mm_acc[2 * b + threadIdx.x] = 0u;
   const MT* m = mask + (size_t)b * Nm;
   const int base = chunk * PC_CHUNK + threadIdx.x * PC_ITEMS;
   const int c = (base < Nm) ? __popc(flags16(m, base, Nm)) : 0;
@@ -149,17 +144,9 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     const MT* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
     int W, int HW, double xs, double ys, int identity_scale, int nchunks, const int* __restrict__ counts,
     float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid, int32_t* __restrict__ vj_flat,
-    float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc, float* __restrict__ minmax) {
+    float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
-  if (mm_acc != nullptr && chunk == 0 && threadIdx.x == 0) {
-    // min / max of gt collected by prep_count_kernel -> floats for the scoring passes; accumulators back to zero
-    const unsigned int omin = ~mm_acc[2 * b], omax = mm_acc[2 * b + 1];
-    minmax[2 * b] = mm_acc[2 * b] ? ordered_to_float(omin) : 3.402823466e38f;
-    minmax[2 * b + 1] = mm_acc[2 * b + 1] ? ordered_to_float(omax) : -3.402823466e38f;
-    mm_acc[2 * b] = 0u;
-    mm_acc[2 * b + 1] = 0u;
-  }
   int pre = 0, all = 0;
   for (int i = threadIdx.x; i < nchunks; i += PC_THREADS) {
     const int c = counts[b * nchunks + i];
@@ -170,6 +157,7 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   const int prefix = block_sum_int(pre, s_warp);
   float2* tab = table + (size_t)b * table_stride;
   const float* g = gt + (size_t)b * HW;
+  MinMaxAcc mm;
   if (identity_scale && total == Nm) {
     const float* s = pred + (size_t)b * HW;
     const bool vec = ((Nm & 3) == 0) && ((table_stride & 1) == 0) &&
@@ -187,17 +175,28 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
           const float4 a = __ldg(g4 + q), c = __ldg(s4 + q);
           t4[2 * q] = make_float4(a.x, c.x, a.y, c.y);
           t4[2 * q + 1] = make_float4(a.z, c.z, a.w, c.w);
+          if (mm_acc != nullptr) { mm.add(a.x); mm.add(a.y); mm.add(a.z); mm.add(a.w); }
         }
       }
     } else {
 #pragma unroll 4
       for (int i = 0; i < PC_ITEMS; ++i) {
         const int j = chunk * PC_CHUNK + i * PC_THREADS + threadIdx.x;
-        if (j < Nm) tab[j] = make_float2(__ldg(g + j), __ldg(s + j));
+        if (j < Nm) {
+          const float gv = __ldg(g + j);
+          tab[j] = make_float2(gv, __ldg(s + j));
+          if (mm_acc != nullptr) mm.add(gv);
+        }
       }
     }
+    if (mm_acc != nullptr) mm.flush(mm_acc + 2 * b);
     if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
     return;
+  }
+  if (mm_acc != nullptr) {
+    // holed / scaled image: the table pass below reads gt at valid pixels only; np.amin / np.amax run over ALL pixels
+    for (int i = chunk * PC_THREADS + threadIdx.x; i < HW; i += gridDim.x * PC_THREADS) mm.add(__ldg(g + i));
+    mm.flush(mm_acc + 2 * b);
   }
   if (grad_valid != nullptr) {   // holed image in valid-index mode: clear its accumulators (valid count <= Nm)
     float* gv = grad_valid + (size_t)b * table_stride;
@@ -587,7 +586,7 @@ using namespace pld;
 template <typename MT>
 static int launch_prep(const MT* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
                        int* counts, float2* table, size_t tstride, int32_t* nv, int32_t* vj_flat, float* grad_valid,
-                       float* grad, cudaStream_t st, unsigned int* mm_acc = nullptr, float* minmax = nullptr) {
+                       float* grad, cudaStream_t st, unsigned int* mm_acc = nullptr) {
   const int HW = H * W, Nm = Hm * Wm;
   const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
   dim3 grid((unsigned)nchunks, (unsigned)B);
@@ -602,12 +601,12 @@ static int launch_prep(const MT* mask, const float* gt, const float* pred, int B
     tail = (int)(gtotal - n4 * 4);
   }
   prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail,
-                                                     gt, HW, mm_acc);
+                                                     mm_acc);
   PLD_CHECK_LAUNCH();
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
   prep_build_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv, vj_flat, grad_valid, mm_acc, minmax);
+                                                table, tstride, nv, vj_flat, grad_valid, mm_acc);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
@@ -746,7 +745,6 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     char* psb = (char*)ctx->d_scratch;
     int* pcounts = (int*)(psb + o_counts);
     int32_t* pnv = n_valid ? n_valid : (int32_t*)(psb + o_nv);
-    float* pminmax = (float*)(psb + o_mm);
     float2* ptable = (float2*)(psb + o_ptab);
     const int pcap = lists_per_image_cap(ctx->num_sms, B);
     prc = ctx->ensure_partials(pcap * B + B);
@@ -759,7 +757,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
       pmm = ctx->d_mm_acc;
     }
     prc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, pcounts, ptable, tstride, pnv, nullptr, nullptr, grad, st,
-                      pmm, pminmax);
+                      pmm);
     if (prc) return prc;
     ListParams P = {};
     P.gt = gt; P.pred = pred ? pred : gt; P.n_valid = pnv; P.table = ptable; P.table_stride = tstride;
@@ -769,7 +767,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
     P.image_base = image_base;
     if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
-    P.score_cfg = make_score_cfg(pminmax, strategy, threshold, equality_penalty, promotion);
+    P.score_cfg = make_score_cfg(nullptr, strategy, threshold, equality_penalty, promotion);
+    P.score_cfg.gt_minmax_enc = pmm;
     const int plow = (promotion == PLD_PROMOTION_NEP50 && strategy != PLD_STRATEGY_INFORMATION) ? 1 : 0;
     uint32_t* porder = nullptr;
     prc = pilot_select(P, R, plow, psb + o_pilot, order_out, ctx->num_sms, &porder, st);
@@ -833,8 +832,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     if (rc) return rc;
     mm_acc = ctx->d_mm_acc;
   }
-  rc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, counts, table, tstride, nv, nullptr, nullptr, grad, st, mm_acc,
-                   minmax);
+  rc = launch_prep(mask, gt, pred ? pred : gt, B, Hm, Wm, H, W, counts, table, tstride, nv, nullptr, nullptr, grad, st, mm_acc);
   if (rc) return rc;
 
   // 2. scoring pass over the n candidates of every image: ordered scores only
@@ -847,7 +845,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   P.image_base = image_base;
   if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
   P.score_keys = keys;
-  P.score_cfg = make_score_cfg(minmax, strategy, threshold, equality_penalty, promotion);
+  P.score_cfg = make_score_cfg(nullptr, strategy, threshold, equality_penalty, promotion);
+  P.score_cfg.gt_minmax_enc = mm_acc;
   const bool radix_select = !select_small_fits(n);
   const bool fused_hist = K <= 16;     // the thread-per-list scoring kernel takes the first histogram of the selection
   if (radix_select) {

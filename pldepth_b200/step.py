@@ -8,6 +8,7 @@ reused, so a step is three kernel launches on the current stream (core sampler; 
 their scoring pass and top-R selection), no host sync.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -34,6 +35,7 @@ class FusedPLStep(object):
         self.step_index = int(first_step)
         self._ctx = context
         self._buf = None
+        self._validated = {}
         if strategy not in ("purely", "masked", "thresholded", "information"):
             raise ValueError("unknown strategy %r" % (strategy,))
         self.strategy = strategy
@@ -112,10 +114,31 @@ class FusedPLStep(object):
         return gt, mask, pred
 
     def _run(self, gt, mask, pred, out=None):
-        gt, mask, pred = self._validate(gt, mask, pred, out)
+        # validation is cached per set of tensor objects (a training loop passes the same buffers every step; the
+        # checks cost more host time than the launches of a step).  Weak references: nothing is kept alive.
+        key = (id(gt), id(mask), id(pred), id(out))
+        seen = self._validated.get(key)
+        if seen is not None and seen[0]() is gt and seen[1]() is mask and seen[2]() is pred and \
+                seen[3] == (gt.data_ptr(), mask.data_ptr(), pred.data_ptr()):
+            dims, mask_u8 = seen[4], seen[5]
+            if out is not None:     # callers may swap the scalar slots between steps (loss windows)
+                ls = out.get("loss_sum")
+                if not isinstance(ls, torch.Tensor) or ls.dtype != torch.float64 or ls.numel() != 1 or \
+                        ls.device != gt.device:
+                    raise ValueError("out['loss_sum'] must be a float64 tensor of one element on %s" % gt.device)
+        else:
+            g0, m0, p0 = gt, mask, pred
+            gt, mask, pred = self._validate(gt, mask, pred, out)
+            dims = (gt.shape[0], gt.shape[1], gt.shape[2], mask.shape[1], mask.shape[2])
+            mask_u8 = mask.dtype == torch.uint8
+            if all(isinstance(t, torch.Tensor) for t in (g0, m0, p0)) and gt.data_ptr() == g0.data_ptr() \
+                    and pred.data_ptr() == p0.data_ptr() and mask.data_ptr() == m0.data_ptr():
+                if len(self._validated) > 64:
+                    self._validated.clear()
+                self._validated[key] = (weakref.ref(g0), weakref.ref(m0), weakref.ref(p0),
+                                        (g0.data_ptr(), m0.data_ptr(), p0.data_ptr()), dims, mask_u8)
         dev = gt.device
-        B, H, W = gt.shape[0], gt.shape[1], gt.shape[2]
-        Hm, Wm = mask.shape[1], mask.shape[2]
+        B, H, W, Hm, Wm = dims
         buf = out if out is not None else self._buffers(B, H, W, Hm, Wm, dev)
         ctx = self._ctx if self._ctx is not None else Context.current(dev.index or 0)
         lib = ctx.lib
@@ -134,7 +157,7 @@ class FusedPLStep(object):
             self.step_index += 1
             return buf
         # one call: mask analysis + zeroed grad, 8-byte lookup tables, fused list kernel
-        entry = lib.pld_fused_step_m8 if mask.dtype == torch.uint8 else lib.pld_fused_step
+        entry = lib.pld_fused_step_m8 if mask_u8 else lib.pld_fused_step
         check(entry(ctx.handle, p(mask), p(gt), p(pred), B, Hm, Wm, H, W, self.K, self.R, self.seed,
                     self.step_index, self.image_base, ctypes.c_float(scale), p(buf["n_valid"]),
                     p(buf["rankings"]), p(buf["loss"]), p(buf["loss_sum"]), c_void_p(None),

@@ -294,7 +294,7 @@ def test_fused_step_object_with_strategy(cuda_device):
     out = st.run(gt_d, mask_d, pred_d)
     ref = ops.fused_step_scored(mask_d, gt_d, pred_d, K, int(R * 1.5), R, "thresholded", seed=3, offset=0)
     assert torch.equal(out["rankings"], ref["rankings"]) and out["loss"].item() == ref["loss"].item()
-    # long lists fall back to the staged calls inside the same object
+    # long lists: same one-call entry point (group-per-list kernels)
     st20 = FusedPLStep(20, 50, seed=3, strategy="masked")
     out20 = st20.run(gt_d, mask_d, pred_d)
     want_loss, want_grad, _ = lo.hourglass_nll(out20["rankings"].cpu().numpy(), pred, B, 20)

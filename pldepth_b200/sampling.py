@@ -15,7 +15,10 @@ returning only ``int(0.8 * R)`` lists (sampling.py:147-150).
 Random-number modes (constructor keyword ``rng``, an extension):
   * ``"numpy"`` (default): consumes the *global* ``np.random`` MT19937 state exactly as the
     reference's ``np.random.randint(M)`` calls do (sampling.py:113) -- same seed, same lists,
-    same state afterwards.  Bit-exact drop-in; synchronises once per call.
+    same state afterwards.  Bit-exact drop-in on tie-free depth maps; synchronises once per call.  (Ties -- equal
+    depths inside a list, equal candidate scores -- follow the reversed STABLE argsort: later draw / larger candidate
+    index first.  The reference's ``np.argsort(...)[::-1]`` is unstable for more than 16 elements, so on quantised
+    depth maps its tie order is build-dependent and may differ.)
   * ``"mt19937"``: same stream, generated on the device from ``seed`` (``np.random.seed(seed)``
     equivalent) -- no host RNG involved.
   * ``"philox"``: counter-based Philox4x32-10 keyed by ``seed``; the throughput mode

@@ -86,29 +86,64 @@ def algorithmic_bytes(B, HW, L, K):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU every 200 ms."""
+    """Samples SM clocks / throttle reasons of the given GPUs during the timed region: in-process NVML every 20 ms
+    (no process spawn: eight ranks forking nvidia-smi every 200 ms is a measurable host load at N = 8), falling back to
+    the nvidia-smi command line where pynvml is missing.  Only rank 0 samples, for all GPUs of the job."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event-reason bits
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
+        self.indices = list(indices) if isinstance(indices, (list, tuple, range)) else [indices]
+        self.rows = []            # [sm_mhz, max_mhz, power_w, hw, hw_thermal, sw_thermal, sw_power_cap] as strings
         self.stop_flag = threading.Event()
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        for h in self._handles:
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            try:
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = int(get(h))
+            self.rows.append([str(sm), str(mx), "%.1f" % pw] +
+                             ["Active" if bits & b else "Not Active" for _, b in self.BITS])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        for ln in out.strip().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self._nvml is not None else 0.2)
 
     def summary(self):
         if not self.rows:
@@ -118,7 +153,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source, "gpus": len(self.indices)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -504,8 +539,10 @@ def run_b200(args):
     n_k = max(5, min(args.steps, 50))
     k_ms, seq_ms = m.kernel_alone(n_k)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # rank 0 samples the clocks of every GPU of the job (one process per GPU, GPU index == local rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])
+    if rank == 0:
+        sampler.start()
     launches0 = _lib.launch_count()
     red0 = m.reductions
     sampler.rows.clear()
@@ -530,7 +567,8 @@ def run_b200(args):
             m.one_step(i)
     m.barrier()
     sampler.stop_flag.set()
-    sampler.join(timeout=3)
+    if rank == 0:
+        sampler.join(timeout=3)
     m.check()
     clocks = sampler.summary()
 

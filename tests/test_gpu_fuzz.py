@@ -16,7 +16,8 @@ def random_case(rs):
     B = int(rs.randint(1, 5))
     H, W = int(rs.randint(5, 72)), int(rs.randint(5, 72))
     scaled = rs.rand() < 0.25
-    Hm, Wm = (int(rs.randint(3, H + 1)), int(rs.randint(3, W + 1))) if scaled else (H, W)
+    # masks coarser AND finer than the image (x_scale > 1 / < 1, sampling.py:124-129)
+    Hm, Wm = (int(rs.randint(3, 2 * H)), int(rs.randint(3, 2 * W))) if scaled else (H, W)
     K = int(rs.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 17, 20, 31, 33, 48, 64, 65, 100]))
     n = int(rs.randint(1, 700 if K <= 16 else 60))
     gt = np.stack([((rs.permutation(H * W) + 0.5) / (H * W)).astype(np.float32).reshape(H, W) for _ in range(B)])

@@ -146,14 +146,16 @@ def test_fused_equals_sample_then_loss(cuda_device, K, n):
 
 @pytest.mark.parametrize("K,n", [(1, 50), (2, 400), (5, 1500), (8, 700), (16, 300), (17, 90), (50, 150), (200, 30),
                                  (512, 9)])
-@pytest.mark.parametrize("geometry", ["full", "holes", "scaled"])
+@pytest.mark.parametrize("geometry", ["full", "holes", "scaled", "finer", "finer-rows"])
 def test_one_call_step_equals_staged_calls(cuda_device, K, n, geometry):
     """pld_fused_step (lookup tables + fused kernel) == pld_mask_compact + pld_fused_sample_loss_bwd:
-    rankings and per-list NLL bit for bit, gradient within tolerance, for full / holed / down-scaled masks."""
+    rankings and per-list NLL bit for bit, gradient within tolerance, for full / holed / down-scaled masks and for
+    masks FINER than the image (x_scale < 1, sampling.py:124-129: several valid mask pixels map to one image pixel, whose
+    gradient contributions must accumulate -- with and without materialised rankings)."""
     from pldepth_b200 import ops
     from tests.test_gpu_sampler import make_maps
     B, H, W = 3, 40, 48
-    Hm, Wm = (20, 16) if geometry == "scaled" else (H, W)
+    Hm, Wm = {"scaled": (20, 16), "finer": (60, 96), "finer-rows": (80, 48)}.get(geometry, (H, W))
     gt, mask = make_maps(H, W, Hm, Wm, 7 * K, B, hole=(geometry != "full"))
     if geometry == "holes":
         mask[1] = 1.0                           # mix of full and holed images in one batch

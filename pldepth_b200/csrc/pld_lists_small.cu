@@ -11,7 +11,17 @@ template <int K, int SRC, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
-  __shared__ float2 s_stage[8 * 32 * STRIDE];
+  // Emitted rankings leave through the TMA engine: the warp's 32 rows lie contiguously in its staging buffer
+  // (32 * K * 8 bytes; the lanes' 8-byte writes are conflict-free for odd K, two-way for K = 2 mod 4) and ONE
+  // cp.async.bulk shared -> global per warp and iteration writes them, instead of K shared-memory loads + K 8-byte
+  // global stores per lane through the L1TEX path that the gathers and reductions of this kernel saturate.  Two
+  // buffers per warp while they fit (K <= 9).  K = 0 mod 4 keeps the padded rows + plain stores (4- to 16-way conflicts).
+  constexpr bool TMA_ROWS = ((K & 3) != 0) && SRC != SRC_FED_RANK && !SCORE;
+  constexpr int STRIDE_E = TMA_ROWS ? K : STRIDE;       // row stride of the emit path
+  constexpr int NBUF = (TMA_ROWS && K <= 9) ? 2 : 1;
+  __shared__ __align__(128) float2 s_stage[8 * 32 * STRIDE * NBUF];
+  int tma_buf = 0;
+  bool tma_pending = false;
   // scoring pass: the first histogram of the radix top-R selection (top 12 key bits) is taken on the fly
   __shared__ unsigned int s_hist[SCORE ? 4096 : 1];
   const int b = blockIdx.y;
@@ -239,26 +249,48 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           continue;
         }
         if (P.rank_out != nullptr) {
-          float2* st = s_stage + wid * (32 * STRIDE);
-#pragma unroll
-          for (int k = 0; k < K; ++k) st[lane * STRIDE + k] = make_float2((float)p[k], lab[k]);
-          __syncwarp();
           const int warp_first = base + wid * 32;              // first list of this warp
           int cnt = P.n - warp_first;                          // active lists in this warp
           cnt = cnt > 32 ? 32 : cnt;
-          if (cnt > 0) {
-            float2* ro = reinterpret_cast<float2*>(P.rank_out) + ((size_t)b * (size_t)P.n + (size_t)warp_first) * K;
-            const int total = cnt * K;
+          float2* ro = reinterpret_cast<float2*>(P.rank_out) + ((size_t)b * (size_t)P.n + (size_t)warp_first) * K;
+          const bool bulk = TMA_ROWS && cnt == 32 && (reinterpret_cast<uintptr_t>(ro) & 15) == 0;   // warp-uniform
+          float2* st = s_stage + (wid * NBUF + (bulk ? tma_buf : 0)) * (32 * STRIDE_E);
+          if (TMA_ROWS && tma_pending) {
+            // the bulk copy that last read this buffer must be done with it (the other buffer's may still run)
+            if (lane == 0) {
+              if (bulk && NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+          }
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-              const int e = i * 32 + lane;
-              if (e < total) {
-                const int li = e / K, kk = e - li * K;
-                ro[e] = st[li * STRIDE + kk];
+          for (int k = 0; k < K; ++k) st[lane * STRIDE_E + k] = make_float2((float)p[k], lab[k]);
+          if (bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t src = (uint32_t)__cvta_generic_to_shared(st);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t"
+                           "cp.async.bulk.commit_group;"
+                           :: "l"(ro), "r"(src), "r"((uint32_t)(32 * K * sizeof(float2))) : "memory");
+            }
+            tma_pending = true;
+            tma_buf ^= (NBUF - 1);
+          } else {
+            __syncwarp();
+            if (cnt > 0) {
+              const int total = cnt * K;
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                const int e = i * 32 + lane;
+                if (e < total) {
+                  const int li = e / K, kk = e - li * K;
+                  ro[e] = st[li * STRIDE_E + kk];
+                }
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
 
@@ -289,6 +321,8 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
       }
     }
   }
+  if (TMA_ROWS && tma_pending && lane == 0)   // shared memory must outlive the bulk copies that read it
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   if (bad) atomicOr(P.status, bad);
   if (SCORE && P.sel_hist != nullptr) {
     __syncthreads();

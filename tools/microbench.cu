@@ -310,6 +310,12 @@ int main() {
   timeit("gather_global_4B_L1_resident_64KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, 16384, NREG * 8, out); });
   timeit("gather_global_8B_L1_resident_64KB", ops, [&] { k_gather_global<float2><<<grid, 256>>>((float2*)map, 8192, NREG * 8, out); });
   timeit("gather_global_4B_whole_25MB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION * NREG, 1, out); });
+  // every CTA of every SM inside ONE region: what an SM-affine image placement could gain from L1 hits
+  timeit("gather_global_4B_one_region_784KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION, 1, out); });
+  timeit("gather_global_8B_one_region_1.5MB", ops, [&] { k_gather_global<float2><<<grid, 256>>>((float2*)map, REGION, 1, out); });
+  timeit("gather_global_4B_one_region_392KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION / 2, 1, out); });
+  timeit("gather_global_4B_one_region_196KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, REGION / 4, 1, out); });
+  timeit("gather_global_4B_one_region_128KB", ops, [&] { k_gather_global<float><<<grid, 256>>>(map, 32768, 1, out); });
   timeit("red_global_f32_image_major_784KB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION, NREG); });
   timeit("red_global_f32_whole_25MB", ops, [&] { k_red_global<<<grid, 256>>>(map, REGION * NREG, 1); });
 

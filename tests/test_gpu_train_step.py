@@ -65,7 +65,12 @@ def test_criterion_gradient_is_the_step_gradient_and_reaches_the_decoder(cuda_de
     assert err <= 1e-5, err
     for name, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
-        assert p.grad.abs().sum().item() > 0, name
+        if name == "head.bias":
+            # the PL loss is invariant to a shift of all scores (every list's gradient sums to zero), so the bias of
+            # the last layer receives exactly the rounding residue of that sum -- which may be 0.0
+            assert p.grad.abs().sum().item() <= 1e-4 * pred.grad.abs().sum().item(), name
+        else:
+            assert p.grad.abs().sum().item() > 0, name
     # pixels outside the mask are never drawn: no gradient there
     assert (pred.grad[:, 0][mask == 0] == 0).all()
 

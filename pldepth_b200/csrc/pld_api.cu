@@ -58,6 +58,7 @@ static int run_lists(pld_ctx* ctx, ListParams& P, int src, bool loss, int accumu
 static void set_rng(ListParams& P, uint64_t seed, uint64_t offset, int image_base) {
   P.seed_lo = (uint32_t)seed;
   P.seed_hi = (uint32_t)(seed >> 32);
+  philox_round_keys(P.seed_lo, P.seed_hi, P.rk0, P.rk1);
   P.off_lo = (uint32_t)offset;
   P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;

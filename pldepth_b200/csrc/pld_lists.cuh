@@ -57,14 +57,19 @@ __device__ __forceinline__ void launch_offset(const ListParams& P, uint32_t& off
 }
 
 // K Philox draws of list l of image (image_base + b), mapped to [0, M)
-template <int K>
+// RK: Philox round keys taken from the kernel parameters (P.rk0 / P.rk1, constant-bank operands) instead of being
+// advanced in registers: 40 instructions fewer per list, which pays in the ALU-heavy scoring kernels; the
+// gather-bound loss kernel measured 6 % SLOWER with it (80 instead of 93 registers -> a third resident CTA per SM),
+// so it keeps the register form.
+template <int K, bool RK = false>
 __device__ __forceinline__ void draw_philox(const ListParams& P, uint32_t off_lo, uint32_t off_hi16, int b, int l,
                                             uint32_t M, uint32_t thresh, int (&sel)[K]) {
   const DrawStream ds{(uint32_t)l, (uint32_t)(P.image_base + b), off_lo, off_hi16, P.seed_lo, P.seed_hi};
   bool rej = false;
 #pragma unroll
   for (int q = 0; q < (K + 3) / 4; ++q) {
-    const Philox4 r = ds.block((uint32_t)q);
+    const Philox4 r = RK ? philox4x32_10_rk(ds.list, ds.image, (uint32_t)q | off_hi16, off_lo, P.rk0, P.rk1)
+                         : ds.block((uint32_t)q);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -10,6 +10,11 @@ namespace pld {
 template <int K, int SRC, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(const ListParams P) {
   // per-warp staging so the emitted rankings leave as fully coalesced 256-byte rows
+#ifdef PLD_SMALL_RK_ALL
+  constexpr bool SMALL_RK = true;
+#else
+  constexpr bool SMALL_RK = SCORE;             // see draw_philox
+#endif
   constexpr int STRIDE = (K & 1) ? K : K + 1;  // float2 units; odd => conflict-free 8-byte writes
   // Emitted rankings leave through the TMA engine: the warp's 32 rows lie contiguously in its staging buffer
   // (32 * K * 8 bytes; the lanes' 8-byte writes are conflict-free for odd K, two-way for K = 2 mod 4) and ONE
@@ -24,9 +29,16 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
   bool tma_pending = false;
   // scoring pass: the first histogram of the radix top-R selection (top 12 key bits) is taken on the fly
   __shared__ unsigned int s_hist[SCORE ? 4096 : 1];
+  __shared__ double s_lad[SCORE ? 16 : 1];     // information strategy: the image's ladder of expected depths
   const int b = blockIdx.y;
-  if (SCORE && P.sel_hist != nullptr) {
-    for (int i = threadIdx.x; i < 4096; i += 256) s_hist[i] = 0u;
+  if (SCORE) {
+    if (P.score_cfg.strategy == PLD_STRATEGY_INFORMATION && threadIdx.x < K) {
+      if (P.score_cfg.promotion == PLD_PROMOTION_NEP50)
+        fill_ladder<float>(P.score_cfg, b, K, (int)threadIdx.x, reinterpret_cast<float*>(s_lad));
+      else fill_ladder<double>(P.score_cfg, b, K, (int)threadIdx.x, s_lad);
+    }
+    if (P.sel_hist != nullptr)
+      for (int i = threadIdx.x; i < 4096; i += 256) s_hist[i] = 0u;
     __syncthreads();
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
     tab = P.table + (size_t)b * P.table_stride;
     const int l0 = blockIdx.x * 256 + threadIdx.x;
     if (blockIdx.x * 256 < P.n) {
-      draw_philox<K>(P, off_lo, off_hi16, b, philox_list(l0 < P.n ? l0 : P.n - 1), M, thresh, pre_sel);
+      draw_philox<K, SMALL_RK>(P, off_lo, off_hi16, b, philox_list(l0 < P.n ? l0 : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
       for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
     }
@@ -159,12 +171,12 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           const int nbase = base + gridDim.x * 256;
           if (nbase < P.n) {
             const int ln = nbase + threadIdx.x;
-            draw_philox<K>(P, off_lo, off_hi16, b, philox_list(ln < P.n ? ln : P.n - 1), M, thresh, pre_sel);
+            draw_philox<K, SMALL_RK>(P, off_lo, off_hi16, b, philox_list(ln < P.n ? ln : P.n - 1), M, thresh, pre_sel);
 #pragma unroll
             for (int k = 0; k < K; ++k) pre_t[k] = __ldg(tab + pre_sel[k]);
           }
         } else if (SRC == SRC_PHILOX) {
-          draw_philox<K>(P, off_lo, off_hi16, b, active ? l : P.n - 1, M, thresh, sel);
+          draw_philox<K, SMALL_RK>(P, off_lo, off_hi16, b, active ? l : P.n - 1, M, thresh, sel);
         } else {
           const int32_t* __restrict__ sin = P.sel_in + list_id * K;
 #pragma unroll
@@ -234,8 +246,8 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
           // scoring pass of the score-based strategies: only the ordered score leaves the kernel; the
           // kept lists are redrawn later from their Philox list id (cheaper than storing 8 B/point)
           const double sc = (P.score_cfg.promotion == PLD_PROMOTION_NEP50)
-                                ? score_regs<float, K>(lab, P.score_cfg, b)
-                                : score_regs<double, K>(lab, P.score_cfg, b);
+                                ? score_regs<float, K>(lab, P.score_cfg, b, reinterpret_cast<const float*>(s_lad))
+                                : score_regs<double, K>(lab, P.score_cfg, b, s_lad);
           const bool f32_exact = P.score_cfg.promotion == PLD_PROMOTION_NEP50 &&
                                  P.score_cfg.strategy != PLD_STRATEGY_INFORMATION;
           const uint64_t skey = f32_exact ? score_key_f32((float)sc) : score_key(sc);

@@ -68,11 +68,21 @@ __device__ __forceinline__ int bin_shift(uint64_t t_hi, uint64_t t_lo) {
 // ordered score key of one candidate from its K depths (any order); identical to the scoring branch of
 // lists_small_kernel, so both selections see the same keys
 template <int K>
-__device__ __forceinline__ uint64_t candidate_key(float (&gs)[K], const ScoreCfg& C, int b) {
+__device__ __forceinline__ uint64_t candidate_key(float (&gs)[K], const ScoreCfg& C, int b, const double* lad) {
   sort_desc_floats<K>(gs);
-  const double sc = (C.promotion == PLD_PROMOTION_NEP50) ? score_regs<float, K>(gs, C, b) : score_regs<double, K>(gs, C, b);
+  const double sc = (C.promotion == PLD_PROMOTION_NEP50) ? score_regs<float, K>(gs, C, b, reinterpret_cast<const float*>(lad))
+                                                         : score_regs<double, K>(gs, C, b, lad);
   const bool f32_exact = C.promotion == PLD_PROMOTION_NEP50 && C.strategy != PLD_STRATEGY_INFORMATION;
   return f32_exact ? score_key_f32((float)sc) : score_key(sc);
+}
+
+// the image's ladder of expected depths in shared memory (float or double by promotion); needs a barrier afterwards
+template <int K>
+__device__ __forceinline__ void ladder_to_shared(const ScoreCfg& C, int b, double* s_lad) {
+  if (C.strategy == PLD_STRATEGY_INFORMATION && threadIdx.x < K) {
+    if (C.promotion == PLD_PROMOTION_NEP50) fill_ladder<float>(C, b, K, (int)threadIdx.x, reinterpret_cast<float*>(s_lad));
+    else fill_ladder<double>(C, b, K, (int)threadIdx.x, s_lad);
+  }
 }
 
 struct ImageDraw {
@@ -94,7 +104,7 @@ template <int K>
 __device__ __forceinline__ void issue_depths(const ListParams& P, const ImageDraw& D, uint32_t off_lo, uint32_t off_hi16,
                                              int b, int l, float (&g)[K]) {
   int sel[K];
-  draw_philox<K>(P, off_lo, off_hi16, b, l, D.M, D.thresh, sel);
+  draw_philox<K, true>(P, off_lo, off_hi16, b, l, D.M, D.thresh, sel);
 #pragma unroll
   for (int k = 0; k < K; ++k) g[k] = __ldg(D.depth + 2 * (size_t)sel[k]);
 }
@@ -126,8 +136,11 @@ __device__ __forceinline__ void find_bin_desc(unsigned int* s_hist, unsigned int
 // ---- 1. pilot -------------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(256) pilot_score_kernel(const ListParams P, const PilotParams Q) {
+  __shared__ double s_lad[16];
   const int b = blockIdx.y;
   const int l = blockIdx.x * 256 + threadIdx.x;
+  ladder_to_shared<K>(P.score_cfg, b, s_lad);
+  __syncthreads();
   if (l >= Q.S_pad) return;
   ImageDraw D;
   uint64_t key = 0ull;
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(256) pilot_score_kernel(const ListParams P, co
     launch_offset(P, off_lo, off_hi16);
     float g[K];
     issue_depths<K>(P, D, off_lo, off_hi16, b, l, g);
-    key = candidate_key<K>(g, P.score_cfg, b);
+    key = candidate_key<K>(g, P.score_cfg, b, s_lad);
   }
   Q.pilot_keys[(size_t)b * Q.S_pad + l] = key;
 }
@@ -231,8 +244,10 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
                                                                                                  int only_flagged) {
   __shared__ int s_cnt[2];
   __shared__ unsigned int s_hist[RS_BINS];
+  __shared__ double s_lad[16];
   const int b = blockIdx.y;
   if (only_flagged && Q.flags[b] == 0) return;
+  ladder_to_shared<K>(P.score_cfg, b, s_lad);
   for (int i = threadIdx.x; i < RS_BINS; i += 256) s_hist[i] = 0u;
   if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
   __syncthreads();
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
     for (int j = 0; j < LPT; ++j) {
       const int l = base + j * 256 + threadIdx.x;
       const bool active = l < n;
-      const uint64_t key = candidate_key<K>(gs[j], P.score_cfg, b);
+      const uint64_t key = candidate_key<K>(gs[j], P.score_cfg, b, s_lad);
       const bool sure = active && key > t_hi;
       const bool band = active && !sure && key >= t_lo;
       const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);

@@ -28,6 +28,11 @@ struct ScoreCfg {
   int promotion;                   // PLD_PROMOTION_*
   double thr_hi, thr_lo, penalty;  // legacy (float64) thresholds
   float thr_hi_f, thr_lo_f;        // nep50 (float32) thresholds
+  // float32 relation test without a division (relation_equal): for a >= b > 0 the ratio r = RN(a / b) is >= 1 > thr_lo,
+  // and  a < b * c_in  =>  r < thr_hi,   a > b * c_out  =>  r >= thr_hi   (c = thr_hi (1 -+ 2^-20): far outside the
+  // half-ulp in which rounding decides); anything in between takes the exact division.  0 = off.
+  float c_in, c_out;
+  int fast_rel;
 };
 
 inline ScoreCfg make_score_cfg(const float* gt_minmax, int strategy, double threshold, double penalty, int promotion) {
@@ -41,13 +46,20 @@ inline ScoreCfg make_score_cfg(const float* gt_minmax, int strategy, double thre
   c.thr_hi_f = (float)c.thr_hi;
   c.thr_lo_f = (float)c.thr_lo;
   c.penalty = penalty;
+  c.c_in = (float)(c.thr_hi * (1.0 - 9.5367431640625e-07));
+  c.c_out = (float)(c.thr_hi * (1.0 + 9.5367431640625e-07));
+  c.fast_rel = (c.thr_hi_f > 1.0f && c.thr_lo_f < 1.0f && c.thr_hi_f < 1e30f && c.c_in < c.thr_hi_f && c.c_out > c.thr_hi_f) ? 1 : 0;
   return c;
 }
 
 template <typename T>
 __device__ __forceinline__ bool relation_equal(float g1, float g2, const ScoreCfg& P) {
   if (sizeof(T) == 4) {
-    const float r = __fdiv_rn(__fadd_rn(g1, 1e-10f), __fadd_rn(g2, 1e-10f));
+    const float a = __fadd_rn(g1, 1e-10f), c = __fadd_rn(g2, 1e-10f);
+    // decided without dividing in all but ~2^-19 of the cases (ScoreCfg::c_in); NaNs fail every test and divide
+    const bool in = a < __fmul_rn(c, P.c_in), out = a > __fmul_rn(c, P.c_out);
+    if (P.fast_rel != 0 && a >= c && c > 1e-30f && a < 1e30f && (in || out)) return in;
+    const float r = __fdiv_rn(a, c);
     return !(r >= P.thr_hi_f) && !(r <= P.thr_lo_f);
   } else {
     const double r = __ddiv_rn(__dadd_rn((double)g1, 1e-10), __dadd_rn((double)g2, 1e-10));
@@ -74,6 +86,14 @@ __device__ __forceinline__ void ladder_setup(const ScoreCfg& C, int b, int K, T&
   stop = (T)mx;
   delta = Arith<T>::sub(stop, start);
   step = Arith<T>::div(delta, (T)K);
+}
+
+// the K expected depths of one image (information strategy), computed once instead of per list
+template <typename T>
+__device__ __forceinline__ void fill_ladder(const ScoreCfg& C, int b, int K, int k, T* out) {
+  T start, stop, delta, step;
+  ladder_setup<T>(C, b, K, start, stop, delta, step);
+  out[k] = ladder<T>(k, K, start, stop, delta, step);
 }
 
 // NumPy pairwise summation (umath loops_utils.h pairwise_sum): n < 8 sequential; n <= 128 eight
@@ -151,18 +171,19 @@ __device__ __forceinline__ double score_list(const G& g, int K, const ScoreCfg& 
 }
 
 // Same arithmetic for a list held in registers (compile-time K <= 16, fully unrolled).
+// `lad`: the image's ladder (fill_ladder) when the caller precomputed it, else null.
 template <typename T, int K>
-__device__ __forceinline__ double score_regs(const float (&g)[K], const ScoreCfg& C, int b) {
+__device__ __forceinline__ double score_regs(const float (&g)[K], const ScoreCfg& C, int b, const T* lad = nullptr) {
   static_assert(K <= 16, "register scoring supports K <= 16");
   using A = Arith<T>;
   double score;
   if (C.strategy == PLD_STRATEGY_INFORMATION) {
-    T start, stop, delta, step;
-    ladder_setup<T>(C, b, K, start, stop, delta, step);
+    T start = (T)0, stop = (T)0, delta = (T)0, step = (T)0;
+    if (lad == nullptr) ladder_setup<T>(C, b, K, start, stop, delta, step);
     T chi[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const T e = ladder<T>(k, K, start, stop, delta, step);
+      const T e = lad != nullptr ? lad[k] : ladder<T>(k, K, start, stop, delta, step);
       const T d = A::sub((T)g[k], e);
       chi[k] = A::div(A::mul(d, d), e);
     }

@@ -662,6 +662,7 @@ static int fused_step_impl(pld_ctx* ctx, const MT* mask, const float* gt, const 
   P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
   P.B = B; P.HW = HW; P.valid_stride = 0; P.n = n; P.K = K; P.scale = scale;
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+  philox_round_keys(P.seed_lo, P.seed_hi, P.rk0, P.rk1);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
   P.grad_valid = grad_valid;
@@ -764,6 +765,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
     P.B = B; P.HW = HW; P.n = n; P.K = K; P.scale = scale;
     P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+  philox_round_keys(P.seed_lo, P.seed_hi, P.rk0, P.rk1);
     P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
     P.image_base = image_base;
     if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;
@@ -841,6 +843,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   P.partials = ctx->d_partials; P.ticket = ctx->d_ticket; P.status = ctx->d_status;
   P.B = B; P.HW = HW; P.n = n; P.K = K; P.scale = scale;
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+  philox_round_keys(P.seed_lo, P.seed_hi, P.rk0, P.rk1);
   P.off_lo = (uint32_t)offset; P.off_hi16 = (uint32_t)((offset >> 32) & 0xFFFFu) << 16;
   P.image_base = image_base;
   if (ctx->use_device_offset) P.offset_dev = ctx->d_offset;

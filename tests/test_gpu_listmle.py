@@ -185,6 +185,49 @@ def test_one_call_step_equals_staged_calls(cuda_device, K, n, geometry):
     assert_close(grad3.cpu().numpy(), want_grad, "gradient without emitted rankings")
 
 
+@pytest.mark.parametrize("K,n", [(17, 300), (24, 200), (33, 300), (50, 400), (56, 100), (64, 200)])
+@pytest.mark.parametrize("geometry", ["full", "holes"])
+@pytest.mark.parametrize("depths", ["clustered", "tied", "tiny"])
+def test_long_lists_order_on_the_full_depth(cuda_device, K, n, geometry, depths):
+    """ranking_size 17..64 (pld_lists_tab.cu) orders by a truncated depth prefix | draw slot and re-orders a list
+    exactly when two of its depths agree in the prefix.  Depth maps built to collide: a few hundred float32 neighbours (runs of 64 share a prefix),
+    a handful of exactly tied values (ties: later draw first, DESIGN.md "Oracle"), and zero / tiny depths.  The
+    emitted rankings must equal the oracle's on the same draws and the staged kernel's (exact 64-bit keys)."""
+    from pldepth_b200 import ops
+    B, H, W = 2, 24, 28
+    rs = np.random.RandomState(K + len(depths))
+    if depths == "clustered":
+        steps = rs.randint(0, 300, size=(B, H, W))
+        gt = (np.float32(0.5) + steps.astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    elif depths == "tied":
+        gt = rs.choice(np.array([0.125, 0.25, 0.2500001, 0.7, 0.70000005], np.float32), size=(B, H, W)).astype(np.float32)
+    else:
+        gt = (rs.randint(0, 80, size=(B, H, W)).astype(np.float32) * np.float32(2.0 ** -140)).astype(np.float32)
+    mask = (rs.rand(B, H, W) > (0.3 if geometry == "holes" else -1)).astype(np.float32)
+    pred = rs.randn(B, H, W, 1).astype(np.float32)
+    gt_d, pred_d, mask_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, pred, mask))
+    loss, _, grad, rank, pl, nv = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=21, offset=4, want_per_list=True)
+    vf, nv2 = ops.mask_compact(mask_d, H, W)
+    _, sel = ops.sample_lists_philox(gt_d, vf, nv2, K, n, 21, 4, 0, want_sel=True, want_rankings=False)
+    _, _, grad2, rank2, _ = ops.fused_sample_loss_bwd(gt_d, vf, nv2, pred_d, K, n, seed=21, offset=4)
+    ops.check_status(cuda_device)
+    assert torch.equal(rank, rank2)
+    rank_h = rank.cpu().numpy()
+    for b in range(B):
+        want = so.rankings_from_selection(sel[b].cpu().numpy().reshape(-1), so.valid_flat_indices(mask[b], (H, W)),
+                                          gt[b], K)
+        assert np.array_equal(rank_h[b], want)
+    want_loss, want_grad, want_pl = lo.hourglass_nll(rank_h, pred, B, K)
+    assert_close(loss.item(), want_loss, "loss")
+    assert_close(pl.cpu().numpy(), want_pl, "per-list NLL")
+    assert_close(grad.cpu().numpy(), want_grad, "gradient")
+    # rankings not materialised (valid-index layout on holed masks): same lists, same loss
+    loss3, _, grad3, _, pl3, _ = ops.fused_step(mask_d, gt_d, pred_d, K, n, seed=21, offset=4, want_rankings=False,
+                                                want_per_list=True)
+    assert torch.equal(pl3, pl) and loss3.item() == loss.item()
+    assert_close(grad3.cpu().numpy(), want_grad, "gradient without emitted rankings")
+
+
 def test_loss_is_deterministic(cuda_device):
     from pldepth_b200 import ops
     y_true, pred = make_problem(4, 64, 64, 5, 5000, 3)

@@ -119,7 +119,8 @@ struct MinMaxAcc {
 
 template <typename MT>
 __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __restrict__ mask, int Nm, int nchunks,
-                                                               int* __restrict__ counts, float4* __restrict__ grad4,
+                                                               int* __restrict__ counts, uint16_t* __restrict__ bits,
+                                                               float4* __restrict__ grad4,
                                                                size_t grad_n4, float* __restrict__ grad_tail,
                                                                int grad_tail_n, unsigned int* __restrict__ mm_acc) {
   __shared__ int s_warp[PC_THREADS / 32];
@@ -128,7 +129,11 @@ __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __rest
   if (mm_acc != nullptr && chunk == 0 && threadIdx.x < 2) mm_acc[2 * b + threadIdx.x] = 0u;
   const MT* m = mask + (size_t)b * Nm;
   const int base = chunk * PC_CHUNK + threadIdx.x * PC_ITEMS;
-  const int c = (base < Nm) ? __popc(flags16(m, base, Nm)) : 0;
+  // the validity flags of the thread's 16 pixels are kept as a bit mask (pixel j of the image = bit j & 15 of word
+  // j >> 4): the table build and the gradient expansion read 1/8 byte per pixel instead of the mask again
+  const uint32_t fl = (base < Nm) ? flags16(m, base, Nm) : 0u;
+  bits[((size_t)b * nchunks + chunk) * PC_THREADS + threadIdx.x] = (uint16_t)fl;
+  const int c = __popc(fl);
   const int tot = block_sum_int(c, s_warp);
   if (threadIdx.x == 0) counts[b * nchunks + chunk] = tot;
   if (grad4 != nullptr) {  // zero the dense gradient map (grid-stride, 16-byte stores)
@@ -144,7 +149,8 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     const MT* __restrict__ mask, const float* __restrict__ gt, const float* __restrict__ pred, int Nm, int Wm,
     int W, int HW, double xs, double ys, int identity_scale, int nchunks, const int* __restrict__ counts,
     float2* __restrict__ table, size_t table_stride, int32_t* __restrict__ n_valid, int32_t* __restrict__ vj_flat,
-    float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc) {
+    float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc, const uint32_t* __restrict__ bits32,
+    float* __restrict__ grad_zero) {
   __shared__ int s_warp[PC_THREADS / 32];
   const int b = blockIdx.y, chunk = blockIdx.x;
   int pre = 0, all = 0;
@@ -189,6 +195,25 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
         }
       }
     }
+    if (grad_zero != nullptr) {
+      // bit-mask mode: only full-mask images accumulate straight into the dense gradient map, so only they need it
+      // cleared (holed images get every pixel written by bits_expand_kernel)
+      float* gz = grad_zero + (size_t)b * HW;
+      if (((reinterpret_cast<uintptr_t>(gz) & 15) == 0) && ((Nm & 3) == 0)) {
+        float4* z4 = reinterpret_cast<float4*>(gz);
+#pragma unroll
+        for (int i = 0; i < PC_ITEMS / 4; ++i) {
+          const int q = chunk * (PC_CHUNK / 4) + i * PC_THREADS + threadIdx.x;
+          if (q * 4 < Nm) z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+#pragma unroll 4
+        for (int i = 0; i < PC_ITEMS; ++i) {
+          const int j = chunk * PC_CHUNK + i * PC_THREADS + threadIdx.x;
+          if (j < Nm) gz[j] = 0.f;
+        }
+      }
+    }
     if (mm_acc != nullptr) mm.flush(mm_acc + 2 * b);
     if (chunk == 0 && threadIdx.x == 0) n_valid[b] = -Nm;
     return;
@@ -209,17 +234,19 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
   // Compaction with lane-consecutive pixels: warp w of the CTA owns pixels
   // [chunk*CHUNK + w*512, +512) as 16 rows of 32; ballots give each valid pixel its rank, so mask
   // reads, gt reads and table writes are all coalesced.
-  const MT* m = mask + (size_t)b * Nm;
+  // The 32 pixels of row i are one 32-bit word of the bit mask written by prep_count_kernel (pixels past the end: 0).
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wbase = chunk * PC_CHUNK + wid * (PC_ITEMS * 32);
   uint32_t bal[PC_ITEMS];
   int wcount = 0;
+  {
+    const uint32_t* bw = bits32 + ((size_t)b * nchunks + chunk) * (PC_THREADS / 2) + wid * PC_ITEMS;
+    const uint32_t mine = lane < PC_ITEMS ? bw[lane] : 0u;
 #pragma unroll
-  for (int i = 0; i < PC_ITEMS; ++i) {
-    const int idx = wbase + i * 32 + lane;
-    const bool v = (idx < Nm) && mask_on(__ldg(m + idx));
-    bal[i] = __ballot_sync(0xffffffffu, v);
-    wcount += __popc(bal[i]);
+    for (int i = 0; i < PC_ITEMS; ++i) {
+      bal[i] = __shfl_sync(0xffffffffu, mine, i);
+      wcount += __popc(bal[i]);
+    }
   }
   __syncthreads();
   if (lane == 0) s_warp[wid] = wcount;
@@ -239,9 +266,10 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
         p = (int)((double)rm * xs) * W + (int)((double)cm * ys);  // sampling.py:115-119
       }
       const int pos = rank + __popc(bal[i] & lt);
-      if (vj_flat != nullptr) {   // valid-index mode: (gt, pred) by valid index + the pixel of every valid index
+      if (grad_valid != nullptr) {   // valid-index mode: (gt, pred) by valid index (+ the pixel of every valid index,
+                                     // unless the gradient is expanded through the bit mask)
         tab[pos] = make_float2(__ldg(g + p), __ldg(pred + (size_t)b * HW + p));
-        vj_flat[(size_t)b * table_stride + pos] = p;
+        if (vj_flat != nullptr) vj_flat[(size_t)b * table_stride + pos] = p;
       } else {
         tab[pos] = make_float2(__int_as_float(p), __ldg(g + p));
       }
@@ -577,16 +605,67 @@ __global__ void __launch_bounds__(256) vj_expand_kernel(const float* __restrict_
   for (int j = blockIdx.x * 256 + threadIdx.x; j < M; j += gridDim.x * 256) gr[vf[j]] = gv[j];
 }
 
+// valid-index mode, mask at image resolution: every pixel of a holed image gets its gradient -- the accumulator of its
+// valid index, or zero -- straight from the bit mask (rank of a pixel = valid pixels before it: chunk counts + popcounts),
+// so neither a pixel list nor a cleared dense map is needed.  Same pixel ownership as prep_build_kernel.
+__global__ void __launch_bounds__(PC_THREADS) bits_expand_kernel(const float* __restrict__ grad_valid,
+                                                                 const uint32_t* __restrict__ bits32,
+                                                                 const int* __restrict__ counts,
+                                                                 const int32_t* __restrict__ n_valid, int nchunks,
+                                                                 size_t table_stride, int HW, float* __restrict__ grad) {
+  __shared__ int s_warp[PC_THREADS / 32];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  if (n_valid[b] < 0) return;   // full mask: the list kernel accumulated straight into the dense map
+  int pre = 0;
+  for (int i = threadIdx.x; i < chunk; i += PC_THREADS) pre += counts[b * nchunks + i];
+  const int prefix = block_sum_int(pre, s_warp);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wbase = chunk * PC_CHUNK + wid * (PC_ITEMS * 32);
+  const uint32_t* bw = bits32 + ((size_t)b * nchunks + chunk) * (PC_THREADS / 2) + wid * PC_ITEMS;
+  const uint32_t mine = lane < PC_ITEMS ? bw[lane] : 0u;
+  uint32_t bal[PC_ITEMS];
+  int wcount = 0;
+#pragma unroll
+  for (int i = 0; i < PC_ITEMS; ++i) {
+    bal[i] = __shfl_sync(0xffffffffu, mine, i);
+    wcount += __popc(bal[i]);
+  }
+  __syncthreads();
+  if (lane == 0) s_warp[wid] = wcount;
+  __syncthreads();
+  int rank = prefix;
+  for (int i = 0; i < wid; ++i) rank += s_warp[i];
+  const uint32_t lt = (1u << lane) - 1u;
+  const float* gv = grad_valid + (size_t)b * table_stride;
+  float* gr = grad + (size_t)b * HW;
+#pragma unroll
+  for (int i = 0; i < PC_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    if (idx < HW) gr[idx] = ((bal[i] >> lane) & 1u) ? gv[rank + __popc(bal[i] & lt)] : 0.f;
+    rank += __popc(bal[i]);
+  }
+}
+
 }  // namespace pld
 
 using namespace pld;
+
+// counts [B, nchunks] followed by the bit mask [B, nchunks, 256] x uint16 (prep_count_kernel -> prep_build_kernel)
+static size_t prep_scratch_bytes(int B, int nchunks) {
+  const size_t c = (sizeof(int) * (size_t)B * nchunks + 255) & ~(size_t)255;
+  return c + sizeof(uint16_t) * (size_t)B * nchunks * PC_THREADS;
+}
+static uint16_t* prep_bits(int* counts, int B, int nchunks) {
+  const size_t c = (sizeof(int) * (size_t)B * nchunks + 255) & ~(size_t)255;
+  return reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(counts) + c);
+}
 
 // Passes 1-2 of both fused steps: valid pixels counted per chunk while `grad` is zeroed, then the per-image lookup
 // tables (layouts: see prep_build_kernel).
 template <typename MT>
 static int launch_prep(const MT* mask, const float* gt, const float* pred, int B, int Hm, int Wm, int H, int W,
                        int* counts, float2* table, size_t tstride, int32_t* nv, int32_t* vj_flat, float* grad_valid,
-                       float* grad, cudaStream_t st, unsigned int* mm_acc = nullptr) {
+                       float* grad, cudaStream_t st, unsigned int* mm_acc = nullptr, bool bit_mode = false) {
   const int HW = H * W, Nm = Hm * Wm;
   const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
   dim3 grid((unsigned)nchunks, (unsigned)B);
@@ -594,19 +673,23 @@ static int launch_prep(const MT* mask, const float* gt, const float* pred, int B
   float4* g4 = nullptr;
   size_t n4 = 0;
   int tail = 0;
-  if (grad != nullptr) {
+  // bit_mode (valid-index mode with the mask at image resolution): `grad` is cleared by prep_build_kernel for
+  // full-mask images and completely written by bits_expand_kernel for holed ones, not here
+  if (grad != nullptr && !bit_mode) {
     PLD_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
     g4 = reinterpret_cast<float4*>(grad);
     n4 = gtotal / 4;
     tail = (int)(gtotal - n4 * 4);
   }
-  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, g4, n4, grad ? grad + n4 * 4 : nullptr, tail,
-                                                     mm_acc);
+  uint16_t* bits = prep_bits(counts, B, nchunks);
+  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, bits, g4, n4, g4 ? grad + n4 * 4 : nullptr,
+                                                     tail, mm_acc);
   PLD_CHECK_LAUNCH();
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
   prep_build_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv, vj_flat, grad_valid, mm_acc);
+                                                table, tstride, nv, vj_flat, grad_valid, mm_acc,
+                                                reinterpret_cast<const uint32_t*>(bits), bit_mode ? grad : nullptr);
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
@@ -628,28 +711,32 @@ static int fused_step_impl(pld_ctx* ctx, const MT* mask, const float* gt, const 
   const int nchunks = (Nm + PC_CHUNK - 1) / PC_CHUNK;
   const size_t tstride = (size_t)(HW > Nm ? HW : Nm);
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t off_counts = 0, off_nv = al(sizeof(int) * (size_t)B * nchunks);
+  const size_t off_counts = 0, off_nv = al(prep_scratch_bytes(B, nchunks));
   const size_t off_tab = off_nv + al(sizeof(int32_t) * (size_t)B);
   // valid-index mode: holed masks, gradient wanted, rankings not materialised (nothing needs the pixel index)
   // -- only while the mask -> image map int(r * H / Hm) is injective (mask not finer than the image): a finer mask sends
   // several valid indices to one pixel, whose contributions must ACCUMULATE, which the dense-map path does
   const bool vj_mode = (rankings == nullptr) && (grad != nullptr) && !ctx->deterministic && Hm <= H && Wm <= W;
+  // ... and with the mask at image resolution the pixel of a valid index follows from the bit mask: no pixel list, no
+  // cleared dense map for holed images (bits_expand_kernel writes every pixel)
+  const bool bit_mode = vj_mode && Hm == H && Wm == W && n > 0;
   const size_t off_vjf = off_tab + al(sizeof(float2) * (size_t)B * tstride);
-  const size_t off_gv = off_vjf + (vj_mode ? al(sizeof(int32_t) * (size_t)B * tstride) : 0);
+  const size_t off_gv = off_vjf + ((vj_mode && !bit_mode) ? al(sizeof(int32_t) * (size_t)B * tstride) : 0);
   const size_t scratch_total = off_gv + (vj_mode ? al(sizeof(float) * (size_t)B * tstride) : 0);
   int rc = ctx->ensure_scratch(scratch_total);
   if (rc) return rc;
   int* counts = (int*)((char*)ctx->d_scratch + off_counts);
   int32_t* nv = n_valid ? n_valid : (int32_t*)((char*)ctx->d_scratch + off_nv);
   float2* table = (float2*)((char*)ctx->d_scratch + off_tab);
-  int32_t* vj_flat = vj_mode ? (int32_t*)((char*)ctx->d_scratch + off_vjf) : nullptr;
+  int32_t* vj_flat = (vj_mode && !bit_mode) ? (int32_t*)((char*)ctx->d_scratch + off_vjf) : nullptr;
   float* grad_valid = vj_mode ? (float*)((char*)ctx->d_scratch + off_gv) : nullptr;
   const int per_image_cap = lists_per_image_cap(ctx->num_sms, B);
   rc = ctx->ensure_partials(per_image_cap * B + B);
   if (rc) return rc;
 
   const size_t gtotal = (size_t)B * HW;
-  rc = launch_prep(mask, gt, pred, B, Hm, Wm, H, W, counts, table, tstride, nv, vj_flat, grad_valid, grad, st);
+  rc = launch_prep(mask, gt, pred, B, Hm, Wm, H, W, counts, table, tstride, nv, vj_flat, grad_valid, grad, st, nullptr,
+                   bit_mode);
   if (rc) return rc;
   if (n == 0) {
     PLD_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
@@ -677,7 +764,11 @@ static int fused_step_impl(pld_ctx* ctx, const MT* mask, const float* gt, const 
   rc = (K <= 16) ? launch_lists_small(P, SRC_PHILOX_TAB, true, ctx->num_sms, st)
                  : launch_lists_large(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
-  if (rc == PLD_OK && vj_mode) {
+  if (rc == PLD_OK && bit_mode) {
+    bits_expand_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PC_THREADS, 0, st>>>(
+        grad_valid, reinterpret_cast<const uint32_t*>(prep_bits(counts, B, nchunks)), counts, nv, nchunks, tstride, HW, grad);
+    PLD_CHECK_LAUNCH();
+  } else if (rc == PLD_OK && vj_mode) {
     int gx = (int)((tstride + 255) / 256);
     if (gx > per_image_cap) gx = per_image_cap;
     vj_expand_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(grad_valid, vj_flat, nv, tstride, HW, grad);
@@ -730,7 +821,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += al(bytes); return o; };
-  const size_t o_counts = take(sizeof(int) * (size_t)B * nchunks);
+  const size_t o_counts = take(prep_scratch_bytes(B, nchunks));
   const size_t o_nv = take(sizeof(int32_t) * B);
   const size_t o_mm = take(sizeof(float) * 2 * B);
   // rankings not materialised, many candidates: sampled-window selection (pld_pilot.cu) -- no key array, no histogram

@@ -450,6 +450,28 @@ class Measurement(object):
         self.torch.cuda.empty_cache()
 
 
+def graph_replay_ms(m, shape, strategy, local_rank, iters=8):
+    """ms per step of the workload of `m` (rankings not materialised) replayed from CUDA graphs, one per buffer set,
+    captured on a private context so that the device-resident Philox offset stays out of everybody else's way."""
+    import torch
+    from pldepth_b200._lib import Context
+    from pldepth_b200.step import FusedPLStep
+    step = FusedPLStep(shape["K"], shape["R"], seed=m.cfg_id, global_batch=shape["B"] * m.world, image_base=m.rank * shape["B"],
+                       emit_rankings=False, strategy=strategy, context=Context(local_rank))
+    graphs = [step.capture(s["gt"], s["mask"], s["pred"])[0] for s in m.sets]
+    for g in graphs:
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        graphs[i % len(graphs)].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    step.check(m.dev)
+    return e0.elapsed_time(e1) / iters
+
+
 def secondary_rows(world, rank, local_rank, peak, peak_src, sm_mhz):
     """The workloads the reference really runs, measured in the same process after the headline (sequential steps,
     few iterations): holed masks, long lists, the config-5 share, the default (InformationScore) strategy."""
@@ -477,6 +499,13 @@ def secondary_rows(world, rank, local_rank, peak, peak_src, sm_mhz):
                          "note": "frac = algorithmic bytes / LAST list kernel of the step; scored strategies run two list "
                                  "passes plus selection, see step_frac" if strategy != "purely" else
                                  "frac = algorithmic bytes / list-kernel time"})
+            if strategy != "purely" and not emit:
+                # the same step replayed from a CUDA graph (FusedPLStep.capture: Philox offset in device memory, fresh
+                # lists on every replay): a scored step is a dozen launches, most of them a few microseconds long
+                try:
+                    rows[-1]["ms_per_step_cuda_graph"] = graph_replay_ms(m, shape, strategy, local_rank)
+                except Exception as exc:
+                    rows[-1]["cuda_graph_error"] = repr(exc)[:200]
             m.free()
             del m
         except Exception as exc:   # a secondary row must never cost the headline line

@@ -55,6 +55,29 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     }                                                                                      \
   } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl may be scheduled while the kernel before
+// it in the stream is still draining -- its CTAs become resident once every CTA of that kernel has started, and block
+// in pdl_sync() until it has completed and its memory is visible -- so the launch latency and the tail of one kernel
+// overlap the ramp-up of the next.  Every kernel launched this way calls pdl_sync() FIRST, on every path (a kernel that
+// returned without waiting would let its own dependents run ahead of the grandparent kernel).  PLD_NO_PDL=1 launches
+// them plainly (A/B runs).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // CTAs per image of the list kernels: enough CTAs per SM that the hardware scheduler evens out the tail
 // (measured at config 2: 8 CTAs/SM 153 us, 4 -> 176 us, 2 -> 202 us; PLD_GRID_MULT overrides for experiments).
 int lists_grid_mult();
@@ -95,6 +118,13 @@ namespace pld {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
+// see launch_pdl: wait for the kernel(s) before this one, then let the kernel after this one be scheduled as soon as
+// every CTA of this grid has started
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   uint32_t u = __float_as_uint(f);
   return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);

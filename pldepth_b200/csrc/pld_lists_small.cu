@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256, PLD_SMALL_MINBLOCKS) lists_small_kernel(c
   // scoring pass: the first histogram of the radix top-R selection (top 12 key bits) is taken on the fly
   __shared__ unsigned int s_hist[SCORE ? 4096 : 1];
   __shared__ double s_lad[SCORE ? 16 : 1];     // information strategy: the image's ladder of expected depths
+  pdl_sync();
   const int b = blockIdx.y;
   if (SCORE) {
     if (P.score_cfg.strategy == PLD_STRATEGY_INFORMATION && threadIdx.x < K) {
@@ -350,7 +351,8 @@ static int launch_small_k(const ListParams& P, dim3 grid, cudaStream_t st) {
   switch (P.K) {
 #define PLD_CASE(KK)                                               \
   case KK:                                                         \
-    lists_small_kernel<KK, SRC, LOSS><<<grid, 256, 0, st>>>(P);    \
+    { cudaError_t e_ = launch_pdl(lists_small_kernel<KK, SRC, LOSS>, grid, dim3(256), 0, st, P); \
+      if (e_ != cudaSuccess) { set_error("launch of lists_small_kernel failed: %s", cudaGetErrorString(e_)); return PLD_ECUDA; } } \
     break;
     PLD_CASE(1) PLD_CASE(2) PLD_CASE(3) PLD_CASE(4) PLD_CASE(5) PLD_CASE(6) PLD_CASE(7) PLD_CASE(8)
     PLD_CASE(9) PLD_CASE(10) PLD_CASE(11) PLD_CASE(12) PLD_CASE(13) PLD_CASE(14) PLD_CASE(15)
@@ -373,7 +375,8 @@ int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st) 
   switch (P.K) {
 #define PLD_CASE(KK)                                                              \
   case KK:                                                                        \
-    lists_small_kernel<KK, SRC_PHILOX_TAB, false, true><<<grid, 256, 0, st>>>(P); \
+    { cudaError_t e_ = launch_pdl(lists_small_kernel<KK, SRC_PHILOX_TAB, false, true>, grid, dim3(256), 0, st, P); \
+      if (e_ != cudaSuccess) { set_error("launch of lists_small_kernel failed: %s", cudaGetErrorString(e_)); return PLD_ECUDA; } } \
     break;
     PLD_CASE(1) PLD_CASE(2) PLD_CASE(3) PLD_CASE(4) PLD_CASE(5) PLD_CASE(6) PLD_CASE(7) PLD_CASE(8)
     PLD_CASE(9) PLD_CASE(10) PLD_CASE(11) PLD_CASE(12) PLD_CASE(13) PLD_CASE(14) PLD_CASE(15)

@@ -113,6 +113,7 @@ __device__ __noinline__ void exact_order(const float2* own, bool gs_layout, uint
 template <int LPL, int IPL, int THREADS, bool LOSS, bool SCORE = false>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS : 4) lists_tab_kernel(const ListParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_sync();
   // Parking buffers.  A lane owns ROW = IPL + 1 consecutive entries (the odd stride keeps its own 8-byte accesses at the
   // two-wavefront minimum); draw slot e of a list group sits at  group_base + e + (e >> log2 IPL).  s_ent: one stage (a
   // warp refills its own rows after it has fetched everything from them); s_aux (selection index): two stages, because
@@ -426,9 +427,9 @@ static int launch_tab_cfg(const ListParams& P, bool loss, int num_sms, cudaStrea
   dim3 grid((unsigned)gx, (unsigned)P.B);
   ListParams Q = P;
   philox_round_keys(P.seed_lo, P.seed_hi, Q.rk0, Q.rk1);
-  if (score) lists_tab_kernel<LPL, IPL, THREADS, false, true><<<grid, THREADS, SMEM, st>>>(Q);
-  else if (loss) lists_tab_kernel<LPL, IPL, THREADS, true><<<grid, THREADS, SMEM, st>>>(Q);
-  else lists_tab_kernel<LPL, IPL, THREADS, false><<<grid, THREADS, SMEM, st>>>(Q);
+  if (score) PLD_CUDA(launch_pdl(lists_tab_kernel<LPL, IPL, THREADS, false, true>, grid, dim3(THREADS), SMEM, st, Q));
+  else if (loss) PLD_CUDA(launch_pdl(lists_tab_kernel<LPL, IPL, THREADS, true>, grid, dim3(THREADS), SMEM, st, Q));
+  else PLD_CUDA(launch_pdl(lists_tab_kernel<LPL, IPL, THREADS, false>, grid, dim3(THREADS), SMEM, st, Q));
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

@@ -137,6 +137,7 @@ __device__ __forceinline__ void find_bin_desc(unsigned int* s_hist, unsigned int
 template <int K>
 __global__ void __launch_bounds__(256) pilot_score_kernel(const ListParams P, const PilotParams Q) {
   __shared__ double s_lad[16];
+  pdl_sync();
   const int b = blockIdx.y;
   const int l = blockIdx.x * 256 + threadIdx.x;
   ladder_to_shared<K>(P.score_cfg, b, s_lad);
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(1024) pilot_rank_kernel(const PilotParams Q, c
   __shared__ unsigned int s_wsum[32];
   __shared__ int s_res[3];
   __shared__ unsigned long long s_or, s_and;
+  pdl_sync();
   const int b = blockIdx.x, tid = threadIdx.x;
   const uint64_t* __restrict__ pk = Q.pilot_keys + (size_t)b * Q.S_pad;
   if (tid == 0) { s_or = 0ull; s_and = ~0ull; }
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
   __shared__ int s_cnt[2];
   __shared__ unsigned int s_hist[RS_BINS];
   __shared__ double s_lad[16];
+  pdl_sync();
   const int b = blockIdx.y;
   if (only_flagged && Q.flags[b] == 0) return;
   ladder_to_shared<K>(P.score_cfg, b, s_lad);
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const PilotParams Q, const 
                                                      int only_flagged) {
   __shared__ unsigned int s_part[256];
   __shared__ int s_tstar, s_base[2], s_k[2];
+  pdl_sync();
   const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   if (only_flagged && Q.flags[b] == 0) return;
   if (n_valid[b] == 0) return;
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(1024) boundary_kernel(const PilotParams Q, con
   __shared__ unsigned int s_wsum[32];
   __shared__ int s_res[3];
   __shared__ int s_count;
+  pdl_sync();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (only_flagged && Q.flags[b] == 0) return;
   if (n_valid[b] == 0) return;
@@ -654,17 +659,18 @@ size_t pilot_select_bytes(int B, int n, int R, int num_sms, size_t* offs) {
 
 template <int K>
 static int pilot_select_k(const ListParams& P, const PilotParams& Q, cudaStream_t st) {
-  pilot_score_kernel<K><<<dim3((unsigned)((Q.S_pad + 255) / 256), (unsigned)P.B), 256, 0, st>>>(P, Q);
+  PLD_CUDA(launch_pdl(pilot_score_kernel<K>, dim3((unsigned)((Q.S_pad + 255) / 256), (unsigned)P.B), dim3(256), 0, st, P, Q));
   PLD_CHECK_LAUNCH();
-  pilot_rank_kernel<<<P.B, 1024, sizeof(uint64_t) * (size_t)Q.S_pad, st>>>(Q, P.n_valid);
+  PLD_CUDA(launch_pdl(pilot_rank_kernel, dim3((unsigned)P.B), dim3(1024), sizeof(uint64_t) * (size_t)Q.S_pad, st, Q,
+                      (const int32_t*)P.n_valid));
   PLD_CHECK_LAUNCH();
   const dim3 grid((unsigned)Q.nseg, (unsigned)P.B);
   for (int round = 0; round < 2; ++round) {
-    score_select_kernel<K><<<grid, 256, 0, st>>>(P, Q, round);
+    PLD_CUDA(launch_pdl(score_select_kernel<K>, grid, dim3(256), 0, st, P, Q, round));
     PLD_CHECK_LAUNCH();
-    gather_kernel<<<grid, 256, 0, st>>>(Q, P.n_valid, round);
+    PLD_CUDA(launch_pdl(gather_kernel, grid, dim3(256), 0, st, Q, (const int32_t*)P.n_valid, round));
     PLD_CHECK_LAUNCH();
-    boundary_kernel<<<P.B, 1024, 0, st>>>(Q, P.n_valid, round, P.status);
+    PLD_CUDA(launch_pdl(boundary_kernel, dim3((unsigned)P.B), dim3(1024), 0, st, Q, (const int32_t*)P.n_valid, round, P.status));
     PLD_CHECK_LAUNCH();
   }
   return PLD_OK;

@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return t_err; }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("PLD_NO_PDL") != nullptr && getenv("PLD_NO_PDL")[0] == '1');
+  return on;
+}
+
 int lists_grid_mult() {
   static int m = 0;
   if (m == 0) {

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(PC_THREADS) prep_count_kernel(const MT* __rest
                                                                size_t grad_n4, float* __restrict__ grad_tail,
                                                                int grad_tail_n, unsigned int* __restrict__ mm_acc) {
   __shared__ int s_warp[PC_THREADS / 32];
+  pdl_sync();
   const int b = blockIdx.y, chunk = blockIdx.x;
   // min / max accumulators of gt (collected by prep_build_kernel, information strategy) start every call from zero
   if (mm_acc != nullptr && chunk == 0 && threadIdx.x < 2) mm_acc[2 * b + threadIdx.x] = 0u;
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(PC_THREADS) prep_build_kernel(
     float* __restrict__ grad_valid, unsigned int* __restrict__ mm_acc, const uint32_t* __restrict__ bits32,
     float* __restrict__ grad_zero) {
   __shared__ int s_warp[PC_THREADS / 32];
+  pdl_sync();
   const int b = blockIdx.y, chunk = blockIdx.x;
   int pre = 0, all = 0;
   for (int i = threadIdx.x; i < nchunks; i += PC_THREADS) {
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(256) vj_expand_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ vj_flat,
                                                         const int32_t* __restrict__ n_valid, size_t table_stride, int HW,
                                                         float* __restrict__ grad) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int M = n_valid[b];
   if (M <= 0) return;   // identity table (negative count) or empty mask
@@ -614,6 +617,7 @@ __global__ void __launch_bounds__(PC_THREADS) bits_expand_kernel(const float* __
                                                                  const int32_t* __restrict__ n_valid, int nchunks,
                                                                  size_t table_stride, int HW, float* __restrict__ grad) {
   __shared__ int s_warp[PC_THREADS / 32];
+  pdl_sync();
   const int b = blockIdx.y, chunk = blockIdx.x;
   if (n_valid[b] < 0) return;   // full mask: the list kernel accumulated straight into the dense map
   int pre = 0;
@@ -682,14 +686,14 @@ static int launch_prep(const MT* mask, const float* gt, const float* pred, int B
     tail = (int)(gtotal - n4 * 4);
   }
   uint16_t* bits = prep_bits(counts, B, nchunks);
-  prep_count_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, Nm, nchunks, counts, bits, g4, n4, g4 ? grad + n4 * 4 : nullptr,
-                                                     tail, mm_acc);
+  PLD_CUDA(launch_pdl(prep_count_kernel<MT>, grid, dim3(PC_THREADS), 0, st, mask, Nm, nchunks, counts, bits, g4, n4,
+                      g4 ? grad + n4 * 4 : nullptr, tail, mm_acc));
   PLD_CHECK_LAUNCH();
   const double xs = (double)H / (double)Hm, ys = (double)W / (double)Wm;
   const int identity_scale = (H == Hm && W == Wm) ? 1 : 0;
-  prep_build_kernel<MT><<<grid, PC_THREADS, 0, st>>>(mask, gt, pred, Nm, Wm, W, HW, xs, ys, identity_scale, nchunks, counts,
-                                                table, tstride, nv, vj_flat, grad_valid, mm_acc,
-                                                reinterpret_cast<const uint32_t*>(bits), bit_mode ? grad : nullptr);
+  PLD_CUDA(launch_pdl(prep_build_kernel<MT>, grid, dim3(PC_THREADS), 0, st, mask, gt, pred, Nm, Wm, W, HW, xs, ys,
+                      identity_scale, nchunks, (const int*)counts, table, tstride, nv, vj_flat, grad_valid, mm_acc,
+                      reinterpret_cast<const uint32_t*>(bits), bit_mode ? grad : (float*)nullptr));
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }
@@ -765,13 +769,15 @@ static int fused_step_impl(pld_ctx* ctx, const MT* mask, const float* gt, const 
                  : launch_lists_large(P, SRC_PHILOX_TAB, true, ctx->num_sms, st);
   ctx->time_end(st);
   if (rc == PLD_OK && bit_mode) {
-    bits_expand_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PC_THREADS, 0, st>>>(
-        grad_valid, reinterpret_cast<const uint32_t*>(prep_bits(counts, B, nchunks)), counts, nv, nchunks, tstride, HW, grad);
+    PLD_CUDA(launch_pdl(bits_expand_kernel, dim3((unsigned)nchunks, (unsigned)B), dim3(PC_THREADS), 0, st,
+                        (const float*)grad_valid, reinterpret_cast<const uint32_t*>(prep_bits(counts, B, nchunks)),
+                        (const int*)counts, (const int32_t*)nv, nchunks, tstride, HW, grad));
     PLD_CHECK_LAUNCH();
   } else if (rc == PLD_OK && vj_mode) {
     int gx = (int)((tstride + 255) / 256);
     if (gx > per_image_cap) gx = per_image_cap;
-    vj_expand_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(grad_valid, vj_flat, nv, tstride, HW, grad);
+    PLD_CUDA(launch_pdl(vj_expand_kernel, dim3((unsigned)gx, (unsigned)B), dim3(256), 0, st, (const float*)grad_valid,
+                        (const int32_t*)vj_flat, (const int32_t*)nv, tstride, HW, grad));
     PLD_CHECK_LAUNCH();
   }
   if (rc == PLD_OK && P.acc != nullptr) rc = launch_acc_finalize(ctx, grad, gtotal, scale, 0, st);

@@ -228,6 +228,42 @@ def test_long_lists_order_on_the_full_depth(cuda_device, K, n, geometry, depths)
     assert_close(grad3.cpu().numpy(), want_grad, "gradient without emitted rankings")
 
 
+@pytest.mark.parametrize("H,W,K,n", [(40, 48, 5, 900), (33, 37, 5, 500), (17, 129, 20, 60), (64, 64, 50, 40)])
+@pytest.mark.parametrize("emit", [True, False])
+def test_uint8_and_bool_masks_equal_float_masks(cuda_device, H, W, K, n, emit):
+    """pld_fused_step_m8: a uint8 / bool mask (nonzero = valid, the HR-WSI masks as stored) gives bit for bit the step
+    of the float32 mask -- emitted and not (bit-mask mode: odd sizes whose rows are neither 16-pixel nor 16-byte
+    aligned, a full-mask image and an empty-hole image in the same batch)."""
+    from pldepth_b200.step import FusedPLStep
+    B = 3
+    rs = np.random.RandomState(H * W + K)
+    gt = rs.rand(B, H, W).astype(np.float32)
+    mask = (rs.rand(B, H, W) > 0.3).astype(np.float32)
+    mask[1] = 1.0
+    mask[2, :, : W // 2] = 0.0
+    pred = rs.randn(B, H, W, 1).astype(np.float32)
+    gt_d, pred_d = torch.from_numpy(gt).to(cuda_device), torch.from_numpy(pred).to(cuda_device)
+    outs = []
+    for m in (torch.from_numpy(mask), torch.from_numpy((mask * 200).astype(np.uint8)), torch.from_numpy(mask > 0)):
+        st = FusedPLStep(K, n, seed=13, emit_rankings=emit)
+        out = st.run(gt_d, m.to(cuda_device), pred_d)
+        st.check(cuda_device)
+        outs.append(out)
+    for o in outs[1:]:
+        assert torch.equal(o["n_valid"], outs[0]["n_valid"])
+        assert o["loss"].item() == outs[0]["loss"].item()
+        if emit:
+            assert torch.equal(o["rankings"], outs[0]["rankings"])
+        assert_close(o["grad"].cpu().numpy(), outs[0]["grad"].cpu().numpy(), "gradient, uint8 vs float32 mask")
+    # ... and the float-mask step is the oracle's
+    if emit:
+        want_loss, want_grad, _ = lo.hourglass_nll(outs[0]["rankings"].cpu().numpy(), pred, B, K)
+        assert_close(outs[0]["loss"].item(), want_loss, "loss")
+        assert_close(outs[0]["grad"].cpu().numpy().reshape(B, -1), want_grad.reshape(B, -1), "gradient")
+    g = outs[0]["grad"].cpu().numpy().reshape(B, H, W)
+    assert (g[mask == 0] == 0).all()          # masked-out pixels: exactly zero, written (not left over)
+
+
 def test_loss_is_deterministic(cuda_device):
     from pldepth_b200 import ops
     y_true, pred = make_problem(4, 64, 64, 5, 5000, 3)

@@ -53,6 +53,7 @@ __device__ __forceinline__ int warp_digit_rank(bool on, int d, int lane, unsigne
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys_a,
                                                              const uint64_t* __restrict__ keys_b, SegInfo seg, int pass,
                                                              int nblk, int* __restrict__ hist) {
+  pdl_sync();
   __shared__ int s_h[RS_BINS];
   const int b = blockIdx.y, tile = blockIdx.x;
   if (seg.skip(b, pass)) return;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
 // digits, eight tiles in flight), then an exclusive scan of the 256 digit totals -> dig_off[b][d]
 __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(int* __restrict__ hist, int* __restrict__ dig_off, SegInfo seg,
                                                           int pass, int nblk) {
+  pdl_sync();
   __shared__ int s_tot[RS_BINS];
   const int b = blockIdx.x;
   if (seg.skip(b, pass)) return;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(uint64_t* __rest
                                                                 SegInfo seg, int pass, int nblk,
                                                                 const int* __restrict__ hist,
                                                                 const int* __restrict__ dig_off) {
+  pdl_sync();
   __shared__ int s_cnt[RS_WARPS][RS_BINS];   // running count while ranking, then the warp's offset inside its digit run
   __shared__ int s_start[RS_BINS];           // first position of the digit inside the digit-ordered tile
   __shared__ int s_gbase[RS_BINS];           // global position of the first element of (this tile, digit)
@@ -225,11 +228,11 @@ int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
   int* dig_off = hist + (size_t)B * nblk * RS_BINS;
   dim3 grid((unsigned)nblk, (unsigned)B);
   for (int pass = first_pass; pass < 8; ++pass) {
-    rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(keys, keys_tmp, seg, pass, nblk, hist);
+    PLD_CUDA(launch_pdl(rs_hist_kernel, dim3(grid), dim3(RS_THREADS), 0, st, keys, keys_tmp, seg, pass, nblk, hist));
     PLD_CHECK_LAUNCH();
-    rs_scan_kernel<<<B, RS_BINS, 0, st>>>(hist, dig_off, seg, pass, nblk);
+    PLD_CUDA(launch_pdl(rs_scan_kernel, dim3(B), dim3(RS_BINS), 0, st, hist, dig_off, seg, pass, nblk));
     PLD_CHECK_LAUNCH();
-    rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(keys, vals, keys_tmp, vals_tmp, seg, pass, nblk, hist, dig_off);
+    PLD_CUDA(launch_pdl(rs_scatter_kernel, dim3(grid), dim3(RS_THREADS), 0, st, keys, vals, keys_tmp, vals_tmp, seg, pass, nblk, hist, dig_off));
     PLD_CHECK_LAUNCH();
   }
   return PLD_OK;
@@ -248,6 +251,7 @@ template <bool FROM_SCORES>
 __global__ void __launch_bounds__(SS_THREADS) sel_small_kernel(const void* __restrict__ src, int n, size_t stride, int R,
                                                               int N2, int ascending_ids, uint32_t* __restrict__ order,
                                                               int32_t* __restrict__ order_out) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char ss_raw[];
   uint64_t* s_key = reinterpret_cast<uint64_t*>(ss_raw);
   uint32_t* s_id = reinterpret_cast<uint32_t*>(ss_raw + sizeof(uint64_t) * (size_t)N2);
@@ -331,9 +335,9 @@ int select_small(const uint64_t* keys, const double* scores, int n, size_t strid
   while (N2 < n) N2 <<= 1;
   const size_t smem = (size_t)N2 * (sizeof(uint64_t) + sizeof(uint32_t));
   if (scores != nullptr)
-    sel_small_kernel<true><<<B, SS_THREADS, smem, st>>>(scores, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out);
+    PLD_CUDA(launch_pdl(sel_small_kernel<true>, dim3(B), dim3(SS_THREADS), smem, st, scores, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out));
   else
-    sel_small_kernel<false><<<B, SS_THREADS, smem, st>>>(keys, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out);
+    PLD_CUDA(launch_pdl(sel_small_kernel<false>, dim3(B), dim3(SS_THREADS), smem, st, keys, n, stride, R, N2, ascending_ids ? 1 : 0, order, order_out));
   PLD_CHECK_LAUNCH();
   return PLD_OK;
 }

@@ -293,6 +293,7 @@ constexpr int SEL_BINS = 4096;
 __global__ void __launch_bounds__(256) sel_init_kernel(uint64_t* prefix, int* remaining, int R, unsigned int* hist, int B,
                                                        unsigned long long* bits_or, unsigned long long* bits_and,
                                                        uint64_t* iprefix) {
+  pdl_sync();
   for (int i = blockIdx.x * 256 + threadIdx.x; i < B * SEL_BINS; i += gridDim.x * 256) hist[i] = 0u;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < B; i += 256) {
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict_
                                                        uint64_t* __restrict__ iprefix, int* __restrict__ remaining,
                                                        int idx_pass, int nbits, const int* __restrict__ n_surv, int R,
                                                        int last) {
+  pdl_sync();
   __shared__ unsigned int s_sum[8];
   const int b = blockIdx.x;
   if (n_surv != nullptr && n_surv[b] == R) {
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(256) sel_find_kernel(unsigned int* __restrict_
 
 __global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restrict__ keys, int n, int pass,
                                                        const uint64_t* __restrict__ prefix, unsigned int* __restrict__ hist) {
+  pdl_sync();
   __shared__ unsigned int s_h[SEL_BINS];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < SEL_BINS; i += 256) s_h[i] = 0u;
@@ -376,6 +379,7 @@ constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
 __global__ void __launch_bounds__(SC_THREADS) sel_count_kernel(const uint64_t* __restrict__ keys, int n, int ntiles,
                                                               const uint64_t* __restrict__ prefix, int* __restrict__ counts) {
+  pdl_sync();
   __shared__ int s_warp[SC_THREADS / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   const uint64_t* k = keys + (size_t)b * n;
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t*
                                                                 uint32_t* __restrict__ vals_s, int* __restrict__ n_surv,
                                                                 unsigned long long* __restrict__ bits_or,
                                                                 unsigned long long* __restrict__ bits_and) {
+  pdl_sync();
   __shared__ int s_warp[SC_THREADS / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   int pre = 0, all = 0;
@@ -456,6 +461,7 @@ __global__ void __launch_bounds__(SC_THREADS) sel_compact_kernel(const uint64_t*
 // zero (compact float32 score keys) its three key passes are skipped and the prefix is completed here
 __global__ void sel_varying_kernel(const unsigned long long* bits_or, const unsigned long long* bits_and,
                                    unsigned long long* varying, int B, uint64_t* prefix, int prefix_shift) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     varying[b] = bits_or[b] ^ bits_and[b];
@@ -475,6 +481,7 @@ __global__ void __launch_bounds__(256) sel2_hist_kernel(const uint64_t* __restri
                                                         int shift, int nbits, const uint64_t* __restrict__ prefix,
                                                         const uint64_t* __restrict__ iprefix, unsigned int* __restrict__ hist,
                                                         int R) {
+  pdl_sync();
   __shared__ unsigned int s_h[SEL_BINS];
   const int b = blockIdx.y;
   const int n = n_surv[b];
@@ -509,6 +516,7 @@ __global__ void __launch_bounds__(SC_THREADS) sel2_count_kernel(const uint64_t* 
                                                                const int* __restrict__ n_surv, size_t stride, int ntiles,
                                                                const uint64_t* __restrict__ prefix,
                                                                const uint64_t* __restrict__ iprefix, int* __restrict__ counts) {
+  pdl_sync();
   __shared__ int s_warp[SC_THREADS / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   const int n = n_surv[b];
@@ -533,6 +541,7 @@ __global__ void __launch_bounds__(SC_THREADS) sel2_compact_kernel(const uint64_t
                                                                  const uint64_t* __restrict__ iprefix,
                                                                  const int* __restrict__ counts, int R,
                                                                  uint32_t* __restrict__ order, int32_t* __restrict__ order_out) {
+  pdl_sync();
   __shared__ int s_warp[SC_THREADS / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   int pre = 0;
@@ -579,6 +588,7 @@ __global__ void __launch_bounds__(256) sel_order_kernel(const uint32_t* __restri
                                                         const unsigned long long* __restrict__ varying,
                                                         const int* __restrict__ n_surv, int n, int R,
                                                         uint32_t* __restrict__ order, int32_t* __restrict__ order_out) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int last = n_surv[b] - 1;
   const unsigned long long v = varying[b];
@@ -950,7 +960,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const bool radix_select = !select_small_fits(n);
   const bool fused_hist = K <= 16;     // the thread-per-list scoring kernel takes the first histogram of the selection
   if (radix_select) {
-    sel_init_kernel<<<(B * SEL_BINS + 255) / 256, 256, 0, st>>>(prefix, remaining, R, shist, B, bits_or, bits_and, iprefix);
+    PLD_CUDA(launch_pdl(sel_init_kernel, dim3((B * SEL_BINS + 255) / 256), dim3(256), 0, st, prefix, remaining, R, shist, B, bits_or, bits_and, iprefix));
     PLD_CHECK_LAUNCH();
     if (fused_hist) P.sel_hist = shist;
   }
@@ -968,38 +978,35 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   if (gsel > per_image_cap) gsel = per_image_cap;
   for (int pass = 0; pass < 3; ++pass) {
     if (pass > 0 || !fused_hist) {   // pass 0 was histogrammed by the thread-per-list scoring kernel
-      sel_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(keys, n, pass, prefix, shist);
+      PLD_CUDA(launch_pdl(sel_hist_kernel, dim3(dim3((unsigned)gsel, (unsigned)B)), dim3(256), 0, st, keys, n, pass, prefix, shist));
       PLD_CHECK_LAUNCH();
     }
-    sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, nullptr, remaining, 0, 12, nullptr, 0, 0);
+    PLD_CUDA(launch_pdl(sel_find_kernel, dim3(B), dim3(256), 0, st, shist, prefix, nullptr, remaining, 0, 12, nullptr, 0, 0));
     PLD_CHECK_LAUNCH();
   }
   dim3 tgrid((unsigned)ntiles, (unsigned)B);
-  sel_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt);
+  PLD_CUDA(launch_pdl(sel_count_kernel, dim3(tgrid), dim3(SC_THREADS), 0, st, keys, n, ntiles, prefix, tcnt));
   PLD_CHECK_LAUNCH();
-  sel_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(keys, n, ntiles, prefix, tcnt, k0, v0, n_surv, bits_or, bits_and);
+  PLD_CUDA(launch_pdl(sel_compact_kernel, dim3(tgrid), dim3(SC_THREADS), 0, st, keys, n, ntiles, prefix, tcnt, k0, v0, n_surv, bits_or, bits_and));
   PLD_CHECK_LAUNCH();
   // compact float32 score keys (pld_score.cuh: score_key_f32) carry nothing below bit 32
   const bool low_bits_zero = (promotion == PLD_PROMOTION_NEP50 && strategy != PLD_STRATEGY_INFORMATION);
   const int skip_key_passes = (rankings == nullptr && low_bits_zero) ? 1 : 0;
-  sel_varying_kernel<<<(B + 255) / 256, 256, 0, st>>>(bits_or, bits_and, varying, B, prefix, skip_key_passes ? 28 : 0);
+  PLD_CUDA(launch_pdl(sel_varying_kernel, dim3((B + 255) / 256), dim3(256), 0, st, bits_or, bits_and, varying, B, prefix, skip_key_passes ? 28 : 0));
   PLD_CHECK_LAUNCH();
 
   if (rankings == nullptr) {
     // 4a. nobody sees the order of the kept lists: refine the selection to the exact cut instead of sorting
     static const int kPass[5][3] = {{0, 16, 12}, {0, 4, 12}, {0, 0, 4}, {1, 11, 12}, {1, 0, 11}};  // idx?, shift, bits
     for (int p = skip_key_passes ? 3 : 0; p < 5; ++p) {
-      sel2_hist_kernel<<<dim3((unsigned)gsel, (unsigned)B), 256, 0, st>>>(k0, v0, n_surv, (size_t)n, kPass[p][0], kPass[p][1],
-                                                                         kPass[p][2], prefix, iprefix, shist, R);
+      PLD_CUDA(launch_pdl(sel2_hist_kernel, dim3(dim3((unsigned)gsel, (unsigned)B)), dim3(256), 0, st, k0, v0, n_surv, (size_t)n, kPass[p][0], kPass[p][1], kPass[p][2], prefix, iprefix, shist, R));
       PLD_CHECK_LAUNCH();
-      sel_find_kernel<<<B, 256, 0, st>>>(shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2], n_surv, R,
-                                         p == 4 ? 1 : 0);
+      PLD_CUDA(launch_pdl(sel_find_kernel, dim3(B), dim3(256), 0, st, shist, prefix, iprefix, remaining, kPass[p][0], kPass[p][2], n_surv, R, p == 4 ? 1 : 0));
       PLD_CHECK_LAUNCH();
     }
-    sel2_count_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt);
+    PLD_CUDA(launch_pdl(sel2_count_kernel, dim3(tgrid), dim3(SC_THREADS), 0, st, k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt));
     PLD_CHECK_LAUNCH();
-    sel2_compact_kernel<<<tgrid, SC_THREADS, 0, st>>>(k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt, R, order,
-                                                     order_out);
+    PLD_CUDA(launch_pdl(sel2_compact_kernel, dim3(tgrid), dim3(SC_THREADS), 0, st, k0, v0, n_surv, (size_t)n, ntiles, prefix, iprefix, tcnt, R, order, order_out));
     PLD_CHECK_LAUNCH();
   } else {
     // 4b. full order of the survivors (ascending, stable LSD radix sort; the four low key bytes are skipped when
@@ -1008,7 +1015,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     if (rc) return rc;
     int go = (R + 255) / 256;
     if (go > per_image_cap) go = per_image_cap;
-    sel_order_kernel<<<dim3((unsigned)go, (unsigned)B), 256, 0, st>>>(v0, v1, varying, n_surv, n, R, order, order_out);
+    PLD_CUDA(launch_pdl(sel_order_kernel, dim3(dim3((unsigned)go, (unsigned)B)), dim3(256), 0, st, v0, v1, varying, n_surv, n, R, order, order_out));
     PLD_CHECK_LAUNCH();
   }
   }

@@ -292,6 +292,106 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? PLD_TAB_MINBLOCKS 
       const bool want_eq = info || C.strategy == PLD_STRATEGY_THRESHOLDED;
       const float nxt0 = __shfl_down_sync(0xffffffffu, lab[0], 1, LPL);
       __syncwarp();     // every lane has fetched its payloads: the rows are free
+      if constexpr (LPL * IPL <= 128 && IPL == 8) {
+        if (C.promotion == PLD_PROMOTION_NEP50) {
+          // float32 scores of lists of up to 128 entries, combined by the whole group instead of one lane:
+          //  * per-position terms go to a compact row of floats (sorted position q at s_term[q]), the "equal" relations
+          //    into a bit per position;
+          //  * information: NumPy's pairwise summation of n <= 128 terms IS eight strided accumulators
+          //    r[j] = a[j] + a[8 + j] + ... combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail --
+          //    one accumulator per lane (two for four-lane groups) and an xor-butterfly reproduce it bit for bit
+          //    (IEEE addition is commutative);
+          //  * masked / thresholded: the sum is a strictly sequential chain (penalties interleaved), run by one lane
+          //    from vector loads of the compact row.
+          float* const s_term = reinterpret_cast<float*>(s_ent + grp);
+          float start = 0.f, stop = 0.f, delta = 0.f, step = 0.f;
+          if (info) ladder_setup<float>(C, b, K, start, stop, delta, step);
+          float term[IPL];
+          uint32_t fl = 0u;
+#pragma unroll
+          for (int i = 0; i < IPL; ++i) {
+            const int ppos = gl * IPL + i;
+            const bool on = i < nreal;
+            const float gn = (i + 1 < IPL) ? lab[(i + 1 < IPL) ? i + 1 : i] : nxt0;
+            const bool has_next = ppos + 1 < K;
+            if (on && want_eq && has_next && relation_equal<float>(lab[i], gn, C)) fl |= 1u << i;
+            if (info) term[i] = on ? chi_term<float>(lab[i], ppos, K, start, stop, delta, step) : 0.f;
+            else term[i] = (on && has_next) ? fabsf(__fsub_rn(lab[i], gn)) : 0.f;
+          }
+          {
+            float4* dst = reinterpret_cast<float4*>(s_term + gl * IPL);
+            dst[0] = make_float4(term[0], term[1], term[2], term[3]);
+            dst[1] = make_float4(term[4], term[5], term[6], term[7]);
+          }
+          __syncwarp();
+          double sc;
+          if (info) {
+            const int n8 = K & ~7;            // K >= 17: NumPy's unrolled branch
+            auto strided = [&](int j) {
+              float r = s_term[j];
+#pragma unroll 4
+              for (int q = 8 + j; q < n8; q += 8) r = __fadd_rn(r, s_term[q]);
+              return r;
+            };
+            float res;
+            if constexpr (LPL >= 8) {      // lanes 0..7 of the group hold the eight accumulators
+              float t = strided(gl & 7);
+              t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1, LPL));
+              t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2, LPL));
+              res = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 4, LPL));
+            } else {
+              float ta = strided(gl), tb = strided(gl + 4);
+              ta = __fadd_rn(ta, __shfl_xor_sync(0xffffffffu, ta, 1, LPL));
+              tb = __fadd_rn(tb, __shfl_xor_sync(0xffffffffu, tb, 1, LPL));
+              ta = __fadd_rn(ta, __shfl_xor_sync(0xffffffffu, ta, 2, LPL));
+              tb = __fadd_rn(tb, __shfl_xor_sync(0xffffffffu, tb, 2, LPL));
+              res = __fadd_rn(ta, tb);
+            }
+            for (int q = n8; q < K; ++q) res = __fadd_rn(res, s_term[q]);
+            int cnt = __popc(fl);
+#pragma unroll
+            for (int o = LPL / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o, LPL);
+            sc = (double)(-res);
+            for (int c = 0; c < cnt; ++c) sc = __dadd_rn(sc, C.penalty);
+            if (gl == 0 && active) P.score_keys[list_id] = score_key(sc);
+          } else {
+            // the group's relation bits, position q at bit q & 31 of word q >> 5
+            constexpr int NW = (LPL * IPL + 31) / 32;
+            uint32_t mw[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) mw[w] = ((gl * IPL) >> 5) == w ? fl << ((gl * IPL) & 31) : 0u;
+#pragma unroll
+            for (int o = LPL / 2; o > 0; o >>= 1) {
+#pragma unroll
+              for (int w = 0; w < NW; ++w) mw[w] |= __shfl_xor_sync(0xffffffffu, mw[w], o, LPL);
+            }
+            if (gl == 0) {
+              const bool thr = C.strategy == PLD_STRATEGY_THRESHOLDED;
+              const float pen = (float)C.penalty;
+              const float4* src = reinterpret_cast<const float4*>(s_term);
+              float acc = 0.f;
+#pragma unroll
+              for (int c4 = 0; c4 < (LPL * IPL) / 4; ++c4) {
+                if (c4 * 4 + 1 < K) {     // uniform: some position of this vector has a successor
+                  const float4 v = src[c4];
+                  const float d[4] = {v.x, v.y, v.z, v.w};
+                  const uint32_t m4 = mw[(c4 * 4) >> 5] >> ((c4 * 4) & 31);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (c4 * 4 + u + 1 < K) {
+                      if (thr && ((m4 >> u) & 1u)) acc = __fadd_rn(acc, pen);
+                      acc = __fadd_rn(acc, d[u]);
+                    }
+                  }
+                }
+              }
+              if (active) P.score_keys[list_id] = score_key_f32(acc);
+            }
+          }
+          __syncwarp();   // the combination is done before the rows are refilled
+          return;
+        }
+      }
       auto parts = [&](auto tag) {
         using T = decltype(tag);
         T start = (T)0, stop = (T)0, delta = (T)0, step = (T)0;

@@ -255,7 +255,7 @@ def test_provider_mirror_per_image_and_batched(cuda_device):
 @pytest.mark.parametrize("promotion", ["nep50", "legacy"])
 @pytest.mark.parametrize("K,geometry", [(2, "full"), (5, "holes"), (5, "ties"), (8, "scaled"), (9, "full"), (16, "holes"),
                                         (17, "full"), (20, "holes"), (33, "ties"), (50, "scaled"), (64, "full"),
-                                        (130, "holes"), (300, "full")])
+                                        (100, "ties"), (128, "holes"), (130, "holes"), (300, "full")])
 @pytest.mark.parametrize("n,R", [(700, 333), (8192, 8192), (9000, 4100)], ids=["smem", "smem-max", "radix"])
 def test_scored_step_equals_staged_pipeline(cuda_device, strategy, promotion, K, geometry, n, R):
     """pld_fused_step_scored (score-only pass + radix top-R + redraw) returns the same kept candidates, in

@@ -2,7 +2,8 @@ import sys, torch, numpy as np
 sys.path.insert(0, '/root/repo')
 from pldepth_b200 import ops, synth
 dev = torch.device('cuda', 0)
-B, H, W, K, R = 32, 448, 448, 5, 100000
+import os
+B, H, W, K, R = int(os.environ.get('PS_B', 32)), 448, 448, int(os.environ.get('PS_K', 5)), int(os.environ.get('PS_R', 100000))
 strategy = sys.argv[1] if len(sys.argv) > 1 else "thresholded"
 emit = not (len(sys.argv) > 2 and sys.argv[2] == "no-emit")
 f = {"thresholded": 1.5, "information": 5}[strategy]

@@ -479,7 +479,9 @@ def secondary_rows(world, rank, local_rank, peak, peak_src, sm_mhz):
     plan = [("C2", 0.1, True, "purely"), ("C2", 0.1, False, "purely"), ("C2", 0.0, False, "purely"),
             ("C3", 0.0, True, "purely"), ("C3", 0.0, False, "purely"), ("C5", 0.0, True, "purely"),
             ("C2", 0.0, True, "information"), ("C2", 0.0, False, "information"),
-            ("C2", 0.0, True, "thresholded"), ("C2", 0.0, False, "thresholded")]
+            ("C2", 0.0, True, "thresholded"), ("C2", 0.0, False, "thresholded"),
+            # long lists with the score-based strategies (hyperopt/hyperparams.py:44 sweeps ranking_size to 500)
+            ("C3", 0.0, False, "thresholded"), ("C3", 0.0, False, "information")]
     for name, hole, emit, strategy in plan:
         shape = workload_shape(name)
         try:

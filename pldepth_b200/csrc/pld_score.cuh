@@ -52,6 +52,13 @@ inline ScoreCfg make_score_cfg(const float* gt_minmax, int strategy, double thre
   return c;
 }
 
+// the exact float32 relation of a ratio a / c that the margin test of relation_equal could not decide (one in ~2^19);
+// out of line: kernels that unroll the test dozens of times must not carry a division per copy
+static __device__ __noinline__ bool relation_equal_exact_f32(float a, float c, float thr_hi, float thr_lo) {
+  const float r = __fdiv_rn(a, c);
+  return !(r >= thr_hi) && !(r <= thr_lo);
+}
+
 template <typename T>
 __device__ __forceinline__ bool relation_equal(float g1, float g2, const ScoreCfg& P) {
   if (sizeof(T) == 4) {
@@ -59,8 +66,7 @@ __device__ __forceinline__ bool relation_equal(float g1, float g2, const ScoreCf
     // decided without dividing in all but ~2^-19 of the cases (ScoreCfg::c_in); NaNs fail every test and divide
     const bool in = a < __fmul_rn(c, P.c_in), out = a > __fmul_rn(c, P.c_out);
     if (P.fast_rel != 0 && a >= c && c > 1e-30f && a < 1e30f && (in || out)) return in;
-    const float r = __fdiv_rn(a, c);
-    return !(r >= P.thr_hi_f) && !(r <= P.thr_lo_f);
+    return relation_equal_exact_f32(a, c, P.thr_hi_f, P.thr_lo_f);
   } else {
     const double r = __ddiv_rn(__dadd_rn((double)g1, 1e-10), __dadd_rn((double)g2, 1e-10));
     return !(r >= P.thr_hi) && !(r <= P.thr_lo);

@@ -22,6 +22,8 @@ int launch_acc_finalize(pld_ctx* ctx, float* grad, size_t n, float scale, int ac
 int launch_offset_advance(pld_ctx* ctx, cudaStream_t st);
 int launch_lists_small_score(const ListParams& P, int num_sms, cudaStream_t st);
 int launch_lists_tab_score(const ListParams& P, int num_sms, cudaStream_t st);
+bool score_reg_fits(const ListParams& P);                                     // pld_score_reg.cu
+int launch_score_reg(const ListParams& P, int num_sms, cudaStream_t st);
 int seg_radix_sort(pld_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
                    const int* len_dev, int len_max, size_t stride, int B, int* hist,
                    const unsigned long long* varying, int first_pass, cudaStream_t st);
@@ -964,7 +966,8 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
     PLD_CHECK_LAUNCH();
     if (fused_hist) P.sel_hist = shist;
   }
-  rc = (K <= 16) ? launch_lists_small_score(P, ctx->num_sms, st) : launch_lists_tab_score(P, ctx->num_sms, st);
+  rc = (K <= 16) ? launch_lists_small_score(P, ctx->num_sms, st)
+       : score_reg_fits(P) ? launch_score_reg(P, ctx->num_sms, st) : launch_lists_tab_score(P, ctx->num_sms, st);
   if (rc) return rc;
   P.sel_hist = nullptr;
 

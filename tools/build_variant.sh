@@ -7,7 +7,7 @@ NAME=$1; FLAGS=$2; shift 2
 cd "$(dirname "$0")/../pldepth_b200/csrc"
 mkdir -p build/var_$NAME ../variants
 OBJS=""
-for f in pld_runtime pld_api pld_step pld_eval pld_sort pld_pilot pld_lists_small pld_lists_large pld_lists_tab; do
+for f in pld_runtime pld_api pld_step pld_eval pld_sort pld_pilot pld_lists_small pld_lists_large pld_lists_tab pld_score_reg; do
   [ -f $f.cu ] || continue
   if [[ " $* " == *" $f.cu "* ]]; then
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall -Xptxas -v \

@@ -501,6 +501,13 @@ def secondary_rows(world, rank, local_rank, peak, peak_src, sm_mhz):
                          "note": "frac = algorithmic bytes / LAST list kernel of the step; scored strategies run two list "
                                  "passes plus selection, see step_frac" if strategy != "purely" else
                                  "frac = algorithmic bytes / list-kernel time"})
+            if emit and hole == 0.0 and strategy == "purely":
+                # DRAM bytes of one launch of the list kernel from an ncu --set full capture (profiles/traffic.json)
+                try:
+                    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                        rows[-1]["traffic"] = json.load(f).get(name)
+                except Exception:
+                    rows[-1]["traffic"] = None
             if strategy != "purely" and not emit:
                 # the same step replayed from a CUDA graph (FusedPLStep.capture: Philox offset in device memory, fresh
                 # lists on every replay): a scored step is a dozen launches, most of them a few microseconds long

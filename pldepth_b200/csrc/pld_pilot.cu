@@ -40,7 +40,8 @@ constexpr int RS_BINS = 1 << RS_BITS;
 constexpr int BD_CAP = 4096;       // boundary-bin entries kept in the small list (per image)
 
 struct PilotParams {
-  uint64_t* pilot_keys; // [B, S_pad] sample keys
+  uint64_t* pilot_keys; // [B, pilot_stride] sample keys: the first S of every image
+  size_t pilot_stride;  // S_pad for the pilot's own array; n when the sample is the head of a stored key array
   uint64_t* t_hi;       // [B] keys above are kept for sure
   uint64_t* t_lo;       // [B] keys below are dropped
   int* flags;           // [B] 1 = window missed, image is redone with the trivial window
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) pilot_score_kernel(const ListParams P, co
     issue_depths<K>(P, D, off_lo, off_hi16, b, l, g);
     key = candidate_key<K>(g, P.score_cfg, b, s_lad);
   }
-  Q.pilot_keys[(size_t)b * Q.S_pad + l] = key;
+  Q.pilot_keys[(size_t)b * Q.pilot_stride + l] = key;
 }
 
 // Bucket of descending rank r (0-based) among s_keys[0, N) after `passes` 11-bit digits below bit `top` (all keys agree
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(1024) pilot_rank_kernel(const PilotParams Q, c
   __shared__ unsigned long long s_or, s_and;
   pdl_sync();
   const int b = blockIdx.x, tid = threadIdx.x;
-  const uint64_t* __restrict__ pk = Q.pilot_keys + (size_t)b * Q.S_pad;
+  const uint64_t* __restrict__ pk = Q.pilot_keys + (size_t)b * Q.pilot_stride;
   if (tid == 0) { s_or = 0ull; s_and = ~0ull; }
   __syncthreads();
   unsigned long long vo = 0ull, va = ~0ull;
@@ -313,6 +314,64 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
         bv[pos] = (uint32_t)l;
         atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
       }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Q.cnt_sure[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[0];
+    Q.cnt_band[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[1];
+    if (s_cnt[0]) atomicAdd(Q.tot + b * 4 + 0, s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(Q.tot + b * 4 + 1, s_cnt[1]);
+  }
+  if (s_cnt[1]) {
+    unsigned int* h = Q.hist + (size_t)b * RS_BINS;
+    for (int i = threadIdx.x; i < RS_BINS; i += 256)
+      if (s_hist[i]) atomicAdd(h + i, s_hist[i]);
+  }
+}
+
+// ---- 2'. the same window test over STORED keys (ranking_size > 16: the scoring pass of the long-list kernels leaves a key
+// array, pld_score_reg.cu / pld_lists_tab.cu); same segments, counters and histogram as score_select_kernel
+__global__ void __launch_bounds__(256) classify_keys_kernel(const uint64_t* __restrict__ keys, int n, const PilotParams Q,
+                                                            const int32_t* __restrict__ n_valid, int only_flagged) {
+  __shared__ int s_cnt[2];
+  __shared__ unsigned int s_hist[RS_BINS];
+  pdl_sync();
+  const int b = blockIdx.y;
+  if (only_flagged && Q.flags[b] == 0) return;
+  if (n_valid[b] == 0) return;
+  for (int i = threadIdx.x; i < RS_BINS; i += 256) s_hist[i] = 0u;
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+  __syncthreads();
+  const uint64_t t_hi = Q.t_hi[b], t_lo = Q.t_lo[b];
+  const int bsh = bin_shift(t_hi, t_lo);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const size_t seg = ((size_t)b * Q.nseg + blockIdx.x) * (size_t)Q.seg_cap;
+  uint32_t* sv = Q.sure_v + seg;
+  uint64_t* bk = Q.band_k + seg;
+  uint32_t* bv = Q.band_v + seg;
+  const uint64_t* __restrict__ kb = keys + (size_t)b * (size_t)n;
+  for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+    const int l = base + threadIdx.x;
+    const bool active = l < n;
+    const uint64_t key = active ? kb[l] : 0ull;
+    const bool sure = active && key > t_hi;
+    const bool band = active && !sure && key >= t_lo;
+    const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
+    int base_s = 0, base_b = 0;
+    if (lane == 0) {
+      if (ms) base_s = atomicAdd(&s_cnt[0], __popc(ms));
+      if (mb) base_b = atomicAdd(&s_cnt[1], __popc(mb));
+    }
+    base_s = __shfl_sync(0xffffffffu, base_s, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    if (sure) sv[base_s + __popc(ms & lt)] = (uint32_t)l;
+    if (band) {
+      const int pos = base_b + __popc(mb & lt);
+      bk[pos] = key;
+      bv[pos] = (uint32_t)l;
+      atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
     }
   }
   __syncthreads();
@@ -683,14 +742,11 @@ int pilot_select_init() {
   return PLD_OK;
 }
 
-// P: the scoring-pass parameters of pld_fused_step_scored (table, n candidates, score_cfg, Philox stream);
-// scratch: pilot_select_bytes() bytes.  Leaves the R kept candidate ids of every image in *order_dev (unordered).
-int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, int32_t* order_out, int num_sms,
-                 uint32_t** order_dev, cudaStream_t st) {
+static void pilot_params(int B, int n, int R, int low_bits_zero, void* scratch, int32_t* order_out, int num_sms,
+                         PilotParams& Q) {
   size_t offs[PILOT_NOFFS];
-  pilot_select_bytes(P.B, P.n, R, num_sms, offs);
+  pilot_select_bytes(B, n, R, num_sms, offs);
   char* sb = (char*)scratch;
-  PilotParams Q;
   Q.pilot_keys = (uint64_t*)(sb + offs[0]);
   Q.t_hi = (uint64_t*)(sb + offs[1]); Q.t_lo = (uint64_t*)(sb + offs[2]);
   Q.flags = (int*)(sb + offs[3]); Q.tot = (int*)(sb + offs[4]); Q.hist = (unsigned int*)(sb + offs[5]);
@@ -699,16 +755,25 @@ int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, i
   Q.band_k = (uint64_t*)(sb + offs[9]); Q.band_v = (uint32_t*)(sb + offs[10]);
   Q.bd_k = (uint64_t*)(sb + offs[11]); Q.bd_v = (uint32_t*)(sb + offs[12]);
   Q.order = (uint32_t*)(sb + offs[13]); Q.order_out = order_out;
-  pilot_geometry(P.B, P.n, num_sms, &Q.nseg, &Q.seg_cap);
+  pilot_geometry(B, n, num_sms, &Q.nseg, &Q.seg_cap);
   Q.R = R;
-  Q.S = P.n < PILOT_SAMPLE ? P.n : PILOT_SAMPLE;
+  Q.S = n < PILOT_SAMPLE ? n : PILOT_SAMPLE;
   int pad = 256;
   while (pad < Q.S) pad <<= 1;
   Q.S_pad = pad;
-  const double p = (double)R / (double)P.n, mu = Q.S * p, sigma = sqrt(Q.S * p * (1.0 - p)), z = pilot_z();
+  Q.pilot_stride = (size_t)pad;
+  const double p = (double)R / (double)n, mu = Q.S * p, sigma = sqrt(Q.S * p * (1.0 - p)), z = pilot_z();
   Q.i_hi = (int)floor(mu - z * sigma) - 1;
   Q.i_lo = (int)ceil(mu + z * sigma) + 1;
   Q.low_bits_zero = low_bits_zero;
+}
+
+// P: the scoring-pass parameters of pld_fused_step_scored (table, n candidates, score_cfg, Philox stream);
+// scratch: pilot_select_bytes() bytes.  Leaves the R kept candidate ids of every image in *order_dev (unordered).
+int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, int32_t* order_out, int num_sms,
+                 uint32_t** order_dev, cudaStream_t st) {
+  PilotParams Q;
+  pilot_params(P.B, P.n, R, low_bits_zero, scratch, order_out, num_sms, Q);
   *order_dev = Q.order;
   switch (P.K) {
 #define PLD_CASE(KK) case KK: return pilot_select_k<KK>(P, Q, st);
@@ -719,6 +784,29 @@ int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, i
       set_error("pilot_select: K=%d out of range", P.K);
       return PLD_EINVAL;
   }
+}
+
+// The same selection over a stored key array keys[B, n] (n > PILOT_SAMPLE): the i.i.d. candidates' first 8192 keys are
+// the sample, one cheap pass classifies the rest.  scratch: pilot_select_bytes() bytes.
+int pilot_select_keys(const uint64_t* keys, int B, int n, const int32_t* n_valid, int* status, int R, int low_bits_zero,
+                      void* scratch, int32_t* order_out, int num_sms, uint32_t** order_dev, cudaStream_t st) {
+  PilotParams Q;
+  pilot_params(B, n, R, low_bits_zero, scratch, order_out, num_sms, Q);
+  Q.pilot_keys = const_cast<uint64_t*>(keys);     // read-only here
+  Q.pilot_stride = (size_t)n;
+  *order_dev = Q.order;
+  PLD_CUDA(launch_pdl(pilot_rank_kernel, dim3((unsigned)B), dim3(1024), sizeof(uint64_t) * (size_t)Q.S_pad, st, Q, n_valid));
+  PLD_CHECK_LAUNCH();
+  const dim3 grid((unsigned)Q.nseg, (unsigned)B);
+  for (int round = 0; round < 2; ++round) {
+    PLD_CUDA(launch_pdl(classify_keys_kernel, grid, dim3(256), 0, st, keys, n, Q, n_valid, round));
+    PLD_CHECK_LAUNCH();
+    PLD_CUDA(launch_pdl(gather_kernel, grid, dim3(256), 0, st, Q, n_valid, round));
+    PLD_CHECK_LAUNCH();
+    PLD_CUDA(launch_pdl(boundary_kernel, dim3((unsigned)B), dim3(1024), 0, st, Q, n_valid, round, status));
+    PLD_CHECK_LAUNCH();
+  }
+  return PLD_OK;
 }
 
 }  // namespace pld

@@ -35,6 +35,8 @@ bool pilot_select_fits(int n);
 size_t pilot_select_bytes(int B, int n, int R, int num_sms, size_t* offs);
 int pilot_select(const ListParams& P, int R, int low_bits_zero, void* scratch, int32_t* order_out, int num_sms,
                  uint32_t** order_dev, cudaStream_t st);
+int pilot_select_keys(const uint64_t* keys, int B, int n, const int32_t* n_valid, int* status, int R, int low_bits_zero,
+                      void* scratch, int32_t* order_out, int num_sms, uint32_t** order_dev, cudaStream_t st);
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_ITEMS = 16;
@@ -908,6 +910,11 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   const size_t o_bits = take(sizeof(unsigned long long) * 4 * (size_t)B);
   const size_t o_order = take(sizeof(uint32_t) * (size_t)B * R);
   const size_t o_tab = take(sizeof(float2) * (size_t)B * tstride);
+  // ranking_size > 16, rankings not materialised: the sampled-window selection runs over the stored key array
+  const bool pilot_keys = (rankings == nullptr) && !ctx->deterministic && K > 16 && pilot_select_fits(n) &&
+                          getenv("PLD_NO_PILOT") == nullptr;
+  size_t poffs2[16];
+  const size_t o_pilot2 = pilot_keys ? take(pilot_select_bytes(B, n, R, ctx->num_sms, poffs2)) : 0;
   int rc = ctx->ensure_scratch(off);
   if (rc) return rc;
   char* sb = (char*)ctx->d_scratch;
@@ -959,7 +966,7 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   P.score_keys = keys;
   P.score_cfg = make_score_cfg(nullptr, strategy, threshold, equality_penalty, promotion);
   P.score_cfg.gt_minmax_enc = mm_acc;
-  const bool radix_select = !select_small_fits(n);
+  const bool radix_select = !select_small_fits(n) && !pilot_keys;
   const bool fused_hist = K <= 16;     // the thread-per-list scoring kernel takes the first histogram of the selection
   if (radix_select) {
     PLD_CUDA(launch_pdl(sel_init_kernel, dim3((B * SEL_BINS + 255) / 256), dim3(256), 0, st, prefix, remaining, R, shist, B, bits_or, bits_and, iprefix));
@@ -971,7 +978,14 @@ extern "C" int pld_fused_step_scored(pld_ctx* ctx, const float* mask, const floa
   if (rc) return rc;
   P.sel_hist = nullptr;
 
-  if (!radix_select) {
+  if (pilot_keys) {
+    // 3". unordered top-R set through the sampled window (pld_pilot.cu), sample = the first 8192 stored keys
+    const bool low0 = (promotion == PLD_PROMOTION_NEP50 && strategy != PLD_STRATEGY_INFORMATION);
+    uint32_t* porder = nullptr;
+    rc = pilot_select_keys(keys, B, n, nv, ctx->d_status, R, low0 ? 1 : 0, sb + o_pilot2, order_out, ctx->num_sms, &porder, st);
+    if (rc) return rc;
+    order = porder;
+  } else if (!radix_select) {
     // 3'. few candidates per image (the sizes the reference runs): one shared-memory sort per image
     rc = select_small(keys, nullptr, n, (size_t)n, B, R, rankings == nullptr, order, order_out, st);
     if (rc) return rc;

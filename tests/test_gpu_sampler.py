@@ -474,6 +474,12 @@ def test_scored_step_at_config2_scale(cuda_device, strategy):
     ("information", 8, 12000, 1, "smooth"),
     ("thresholded", 2, 30000, 30000, "ties"),   # R == n: everything is kept
     ("masked", 16, 10000, 2500, "const"),       # one distinct score: the cut is decided by candidate ids alone
+    # ranking_size > 16: the window selection runs over the key array the long-list scoring passes store
+    ("thresholded", 20, 9000, 6000, "smooth"),
+    ("information", 50, 12000, 3000, "smooth"),
+    ("masked", 33, 10000, 2500, "const"),
+    ("thresholded", 64, 8200, 8199, "ties"),
+    ("information", 130, 9000, 100, "ties"),
 ])
 @pytest.mark.parametrize("z", [None, "0", "0.5"])
 def test_sampled_window_selection_keeps_the_exact_set(cuda_device, strategy, K, n, R, kind, z):

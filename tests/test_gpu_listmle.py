@@ -482,6 +482,40 @@ def test_cuda_graph_replay_draws_fresh_lists(cuda_device, strategy):
         ctx.device_offset(False)
 
 
+@pytest.mark.parametrize("strategy,K,R", [("purely", 5, 400), ("information", 5, 3000), ("thresholded", 20, 7000)])
+def test_cuda_graph_replay_without_rankings(cuda_device, strategy, K, R):
+    """The training-step form (rankings not materialised) from a CUDA graph: holed masks run in bit-mask mode, the scored
+    strategies through the sampled-window selection (more than 8192 candidates per image; over the stored keys for
+    K > 16) -- every kernel of those chains is a programmatic dependent launch, which the capture must keep in order.
+    Each replay equals the eager step with the next Philox offset."""
+    from pldepth_b200._lib import Context
+    from pldepth_b200.step import FusedPLStep
+    from tests.test_gpu_sampler import make_maps
+    B, H, W = 2, 48, 40
+    gt, mask = make_maps(H, W, H, W, 9, B)
+    mask[1] = 1.0                                   # one full mask, one holed
+    pred = np.random.RandomState(2).randn(B, H, W, 1).astype(np.float32)
+    gt_d, mask_d, pred_d = (torch.from_numpy(x).to(cuda_device) for x in (gt, mask, pred))
+    ctx = Context(cuda_device.index or 0)           # private context: the device-resident offset stays out of the way
+    st = FusedPLStep(K, R, seed=8, strategy=strategy, emit_rankings=False, context=ctx)
+    st.step_index = 20
+    graph, buf = st.capture(gt_d, mask_d, pred_d)   # warm-up consumed offset 20
+    seen = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        seen.append((buf["loss"].item(), buf["grad"].clone()))
+    st.check(cuda_device)
+    for i, (loss, grad) in enumerate(seen):
+        ref = FusedPLStep(K, R, seed=8, strategy=strategy, emit_rankings=True)
+        ref.step_index = 21 + i
+        out = ref.run(gt_d, mask_d, pred_d)
+        want_loss, want_grad, _ = lo.hourglass_nll(out["rankings"].cpu().numpy(), pred, B, K)
+        assert_close(loss, want_loss, "replayed loss")
+        assert_close(grad.cpu().numpy().reshape(B, -1), want_grad.reshape(B, -1), "replayed gradient")
+    assert seen[0][0] != seen[1][0]
+
+
 def test_pre_gathered_loss_and_standalone_gather(cuda_device):
     """NegativeLogLikelihoodLoss (nll_loss.py:10-29) and prepare_fully_fledged_loss_input (depth_utils.py:39-61)."""
     from pldepth_b200.depth_utils import get_depth_relation, prepare_fully_fledged_loss_input

@@ -47,16 +47,19 @@ struct PilotParams {
   int* flags;           // [B] 1 = window missed, image is redone with the trivial window
   int* tot;             // [B, 4] #sure, #band, #written to the output so far, #boundary entries
   unsigned int* hist;   // [B, RS_BINS] band entries per linear bin of [t_lo, t_hi]
-  int* cnt_sure;        // [B, nseg] entries in every CTA segment
-  int* cnt_band;        // [B, nseg]
-  uint32_t* sure_v;     // [B, nseg * seg_cap] candidate ids kept for sure, segment c at c * seg_cap
-  uint64_t* band_k;     // [B, nseg * seg_cap]
-  uint32_t* band_v;     // [B, nseg * seg_cap]
+  // Every WARP of the scoring pass appends to its own sub-segment (8 per CTA, sub-segment s = cta * 8 + warp at
+  // s * sub_cap): its counters are warp-uniform registers -- no atomic, no broadcast on the critical path (the
+  // shared-memory counters of the first version were 14 % of the pass's stall samples).
+  int* cnt_sure;        // [B, nsub] entries in every sub-segment
+  int* cnt_band;        // [B, nsub]
+  uint32_t* sure_v;     // [B, nsub * sub_cap] candidate ids kept for sure
+  uint64_t* band_k;     // [B, nsub * sub_cap]
+  uint32_t* band_v;     // [B, nsub * sub_cap]
   uint64_t* bd_k;       // [B, BD_CAP] entries of the boundary bin
   uint32_t* bd_v;       // [B, BD_CAP]
   uint32_t* order;      // [B, R] kept candidate ids
   int32_t* order_out;   // [B, R] nullable copy for the caller
-  int R, S, S_pad, i_hi, i_lo, low_bits_zero, nseg, seg_cap;
+  int R, S, S_pad, i_hi, i_lo, low_bits_zero, nseg, seg_cap, nsub, sub_cap;
 };
 
 // linear bin of a band key: (key - t_lo) >> bin_shift, bin_shift chosen so that t_hi lands below RS_BINS
@@ -69,9 +72,10 @@ __device__ __forceinline__ int bin_shift(uint64_t t_hi, uint64_t t_lo) {
 // ordered score key of one candidate from its K depths (any order); identical to the scoring branch of
 // lists_small_kernel, so both selections see the same keys
 template <int K>
-__device__ __forceinline__ uint64_t candidate_key(float (&gs)[K], const ScoreCfg& C, int b, const double* lad) {
+__device__ __forceinline__ uint64_t candidate_key(float (&gs)[K], const ScoreCfg& C, int b, const float* lad_f,
+                                                  const double* lad) {
   sort_desc_floats<K>(gs);
-  const double sc = (C.promotion == PLD_PROMOTION_NEP50) ? score_regs<float, K>(gs, C, b, reinterpret_cast<const float*>(lad))
+  const double sc = (C.promotion == PLD_PROMOTION_NEP50) ? score_regs<float, K>(gs, C, b, lad_f)
                                                          : score_regs<double, K>(gs, C, b, lad);
   const bool f32_exact = C.promotion == PLD_PROMOTION_NEP50 && C.strategy != PLD_STRATEGY_INFORMATION;
   return f32_exact ? score_key_f32((float)sc) : score_key(sc);
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(256) pilot_score_kernel(const ListParams P, co
     launch_offset(P, off_lo, off_hi16);
     float g[K];
     issue_depths<K>(P, D, off_lo, off_hi16, b, l, g);
-    key = candidate_key<K>(g, P.score_cfg, b, s_lad);
+    key = candidate_key<K>(g, P.score_cfg, b, reinterpret_cast<const float*>(s_lad), s_lad);
   }
   Q.pilot_keys[(size_t)b * Q.pilot_stride + l] = key;
 }
@@ -245,16 +249,24 @@ template <int K>
 __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_MINBLOCKS : 2)) score_select_kernel(const ListParams P,
                                                                                                  const PilotParams Q,
                                                                                                  int only_flagged) {
-  __shared__ int s_cnt[2];
   __shared__ unsigned int s_hist[RS_BINS];
   __shared__ double s_lad[16];
+  __shared__ int s_tot[2];
   pdl_sync();
   const int b = blockIdx.y;
   if (only_flagged && Q.flags[b] == 0) return;
   ladder_to_shared<K>(P.score_cfg, b, s_lad);
   for (int i = threadIdx.x; i < RS_BINS; i += 256) s_hist[i] = 0u;
-  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+  if (threadIdx.x < 2) s_tot[threadIdx.x] = 0;
   __syncthreads();
+  // short lists keep the float32 ladder in registers: the shared-memory read per term showed up as 10 % of the stall
+  // samples (short scoreboard) of the information pass
+  float lad_r[K <= 8 ? K : 1];
+  if (K <= 8) {
+#pragma unroll
+    for (int k = 0; k < (K <= 8 ? K : 1); ++k) lad_r[k] = reinterpret_cast<const float*>(s_lad)[k];
+  }
+  const float* lad_f = K <= 8 ? lad_r : reinterpret_cast<const float*>(s_lad);
   ImageDraw D;
   const bool ok = image_draw(P, b, D);      // empty mask: nothing is appended; the redraw pass raises PLD_ST_EMPTY_MASK
   uint32_t off_lo, off_hi16;
@@ -264,10 +276,11 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int n = P.n;
-  const size_t seg = ((size_t)b * Q.nseg + blockIdx.x) * (size_t)Q.seg_cap;
-  uint32_t* sv = Q.sure_v + seg;
-  uint64_t* bk = Q.band_k + seg;
-  uint32_t* bv = Q.band_v + seg;
+  const size_t subseg = (size_t)b * Q.nsub + (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  uint32_t* sv = Q.sure_v + subseg * (size_t)Q.sub_cap;
+  uint64_t* bk = Q.band_k + subseg * (size_t)Q.sub_cap;
+  uint32_t* bv = Q.band_v + subseg * (size_t)Q.sub_cap;
+  int cnt_s = 0, cnt_b = 0;                 // this warp's appends so far (warp-uniform)
   constexpr int LPT = PLD_SCORESEL_LPT;     // lists per thread and iteration: LPT * K gathers in flight per thread
   const int stride = gridDim.x * 256 * LPT;
   float pre[LPT][K];
@@ -296,34 +309,33 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
     for (int j = 0; j < LPT; ++j) {
       const int l = base + j * 256 + threadIdx.x;
       const bool active = l < n;
-      const uint64_t key = candidate_key<K>(gs[j], P.score_cfg, b, s_lad);
+      const uint64_t key = candidate_key<K>(gs[j], P.score_cfg, b, lad_f, s_lad);
       const bool sure = active && key > t_hi;
       const bool band = active && !sure && key >= t_lo;
       const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
-      int base_s = 0, base_b = 0;
-      if (lane == 0) {
-        if (ms) base_s = atomicAdd(&s_cnt[0], __popc(ms));
-        if (mb) base_b = atomicAdd(&s_cnt[1], __popc(mb));
-      }
-      base_s = __shfl_sync(0xffffffffu, base_s, 0);
-      base_b = __shfl_sync(0xffffffffu, base_b, 0);
-      if (sure) sv[base_s + __popc(ms & lt)] = (uint32_t)l;
+      if (sure) sv[cnt_s + __popc(ms & lt)] = (uint32_t)l;
       if (band) {
-        const int pos = base_b + __popc(mb & lt);
+        const int pos = cnt_b + __popc(mb & lt);
         bk[pos] = key;
         bv[pos] = (uint32_t)l;
         atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
       }
+      cnt_s += __popc(ms);
+      cnt_b += __popc(mb);
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Q.cnt_sure[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[0];
-    Q.cnt_band[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[1];
-    if (s_cnt[0]) atomicAdd(Q.tot + b * 4 + 0, s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(Q.tot + b * 4 + 1, s_cnt[1]);
+  if (lane == 0) {
+    Q.cnt_sure[subseg] = cnt_s;
+    Q.cnt_band[subseg] = cnt_b;
+    if (cnt_s) atomicAdd(&s_tot[0], cnt_s);
+    if (cnt_b) atomicAdd(&s_tot[1], cnt_b);
   }
-  if (s_cnt[1]) {
+  const bool any_band = __syncthreads_or(cnt_b != 0);
+  if (threadIdx.x == 0) {   // one global atomic per CTA and counter: hundreds of warps on two addresses would queue up
+    if (s_tot[0]) atomicAdd(Q.tot + b * 4 + 0, s_tot[0]);
+    if (s_tot[1]) atomicAdd(Q.tot + b * 4 + 1, s_tot[1]);
+  }
+  if (any_band) {
     unsigned int* h = Q.hist + (size_t)b * RS_BINS;
     for (int i = threadIdx.x; i < RS_BINS; i += 256)
       if (s_hist[i]) atomicAdd(h + i, s_hist[i]);
@@ -334,23 +346,24 @@ __global__ void __launch_bounds__(256, (K <= 5) ? 4 : ((K <= 8) ? PLD_SCORESEL_M
 // array, pld_score_reg.cu / pld_lists_tab.cu); same segments, counters and histogram as score_select_kernel
 __global__ void __launch_bounds__(256) classify_keys_kernel(const uint64_t* __restrict__ keys, int n, const PilotParams Q,
                                                             const int32_t* __restrict__ n_valid, int only_flagged) {
-  __shared__ int s_cnt[2];
   __shared__ unsigned int s_hist[RS_BINS];
+  __shared__ int s_tot[2];
   pdl_sync();
   const int b = blockIdx.y;
   if (only_flagged && Q.flags[b] == 0) return;
   if (n_valid[b] == 0) return;
   for (int i = threadIdx.x; i < RS_BINS; i += 256) s_hist[i] = 0u;
-  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+  if (threadIdx.x < 2) s_tot[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t t_hi = Q.t_hi[b], t_lo = Q.t_lo[b];
   const int bsh = bin_shift(t_hi, t_lo);
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const size_t seg = ((size_t)b * Q.nseg + blockIdx.x) * (size_t)Q.seg_cap;
-  uint32_t* sv = Q.sure_v + seg;
-  uint64_t* bk = Q.band_k + seg;
-  uint32_t* bv = Q.band_v + seg;
+  const size_t subseg = (size_t)b * Q.nsub + (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  uint32_t* sv = Q.sure_v + subseg * (size_t)Q.sub_cap;
+  uint64_t* bk = Q.band_k + subseg * (size_t)Q.sub_cap;
+  uint32_t* bv = Q.band_v + subseg * (size_t)Q.sub_cap;
+  int cnt_s = 0, cnt_b = 0;
   const uint64_t* __restrict__ kb = keys + (size_t)b * (size_t)n;
   for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
     const int l = base + threadIdx.x;
@@ -359,29 +372,28 @@ __global__ void __launch_bounds__(256) classify_keys_kernel(const uint64_t* __re
     const bool sure = active && key > t_hi;
     const bool band = active && !sure && key >= t_lo;
     const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
-    int base_s = 0, base_b = 0;
-    if (lane == 0) {
-      if (ms) base_s = atomicAdd(&s_cnt[0], __popc(ms));
-      if (mb) base_b = atomicAdd(&s_cnt[1], __popc(mb));
-    }
-    base_s = __shfl_sync(0xffffffffu, base_s, 0);
-    base_b = __shfl_sync(0xffffffffu, base_b, 0);
-    if (sure) sv[base_s + __popc(ms & lt)] = (uint32_t)l;
+    if (sure) sv[cnt_s + __popc(ms & lt)] = (uint32_t)l;
     if (band) {
-      const int pos = base_b + __popc(mb & lt);
+      const int pos = cnt_b + __popc(mb & lt);
       bk[pos] = key;
       bv[pos] = (uint32_t)l;
       atomicAdd(&s_hist[(unsigned int)((key - t_lo) >> bsh)], 1u);
     }
+    cnt_s += __popc(ms);
+    cnt_b += __popc(mb);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Q.cnt_sure[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[0];
-    Q.cnt_band[(size_t)b * Q.nseg + blockIdx.x] = s_cnt[1];
-    if (s_cnt[0]) atomicAdd(Q.tot + b * 4 + 0, s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(Q.tot + b * 4 + 1, s_cnt[1]);
+  if (lane == 0) {
+    Q.cnt_sure[subseg] = cnt_s;
+    Q.cnt_band[subseg] = cnt_b;
+    if (cnt_s) atomicAdd(&s_tot[0], cnt_s);
+    if (cnt_b) atomicAdd(&s_tot[1], cnt_b);
   }
-  if (s_cnt[1]) {
+  const bool any_band = __syncthreads_or(cnt_b != 0);
+  if (threadIdx.x == 0) {   // one global atomic per CTA and counter: hundreds of warps on two addresses would queue up
+    if (s_tot[0]) atomicAdd(Q.tot + b * 4 + 0, s_tot[0]);
+    if (s_tot[1]) atomicAdd(Q.tot + b * 4 + 1, s_tot[1]);
+  }
+  if (any_band) {
     unsigned int* h = Q.hist + (size_t)b * RS_BINS;
     for (int i = threadIdx.x; i < RS_BINS; i += 256)
       if (s_hist[i]) atomicAdd(h + i, s_hist[i]);
@@ -402,7 +414,27 @@ __global__ void __launch_bounds__(256) gather_kernel(const PilotParams Q, const 
   const int ns = Q.tot[b * 4 + 0], nb = Q.tot[b * 4 + 1];
   if (ns > R || ns + nb < R) return;          // missed window: boundary_kernel flags the image
   const int need = R - ns;
-  const int cnt_s = Q.cnt_sure[(size_t)b * Q.nseg + c], cnt_b = Q.cnt_band[(size_t)b * Q.nseg + c];
+  // the CTA's eight warp sub-segments, addressed as ONE virtual array: entry v of the concatenation lives at
+  // sub-segment u (the last one whose prefix count is <= v), offset v - prefix[u]
+  int ps_s[9], ps_b[9];
+  ps_s[0] = 0; ps_b[0] = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    ps_s[u + 1] = ps_s[u] + Q.cnt_sure[(size_t)b * Q.nsub + c * 8 + u];
+    ps_b[u + 1] = ps_b[u] + Q.cnt_band[(size_t)b * Q.nsub + c * 8 + u];
+  }
+  const int cnt_s = ps_s[8], cnt_b = ps_b[8];
+  const int sub_cap = Q.sub_cap;
+  auto vmap = [&](const int (&ps)[9], int v) {
+    int base = 0, off = v;
+#pragma unroll
+    for (int u = 1; u < 8; ++u) {
+      const bool ge = v >= ps[u];
+      base = ge ? u * sub_cap : base;
+      off = ge ? v - ps[u] : off;
+    }
+    return base + off;
+  };
   if (cnt_s == 0 && cnt_b == 0) return;
   // boundary bin: thread t owns bins [8t, 8t + 8), scanned from the top
   int tstar = RS_BINS;                        // need == 0: nothing from the band
@@ -429,14 +461,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const PilotParams Q, const 
   }
   const uint64_t t_hi = Q.t_hi[b], t_lo = Q.t_lo[b];
   const int bsh = bin_shift(t_hi, t_lo);
-  const size_t seg = ((size_t)b * Q.nseg + c) * (size_t)Q.seg_cap;
+  const size_t seg = ((size_t)b * Q.nsub + (size_t)c * 8) * (size_t)sub_cap;
   const uint64_t* __restrict__ bk = Q.band_k + seg;
   const uint32_t* __restrict__ bv = Q.band_v + seg;
   // pass 1: how many of this segment's band entries lie above / inside the boundary bin
   int keep = 0, bd = 0;
   if (need > 0) {
     for (int i = tid; i < cnt_b; i += 256) {
-      const int bin = (int)((bk[i] - t_lo) >> bsh);
+      const int bin = (int)((bk[vmap(ps_b, i)] - t_lo) >> bsh);
       keep += bin > tstar;
       bd += bin == tstar;
     }
@@ -466,7 +498,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const PilotParams Q, const 
   for (int i = tid; i < cnt_s; i += 256) {
     const int pos = obase + i;
     if (pos < R) {
-      const uint32_t v = sv[i];
+      const uint32_t v = sv[vmap(ps_s, i)];
       order[pos] = v;
       if (order_out != nullptr) order_out[pos] = (int32_t)v;
     }
@@ -481,7 +513,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const PilotParams Q, const 
       uint64_t k = 0ull;
       uint32_t v = 0u;
       int bin = -1;
-      if (i < cnt_b) { k = bk[i]; v = bv[i]; bin = (int)((k - t_lo) >> bsh); }
+      if (i < cnt_b) { const int a = vmap(ps_b, i); k = bk[a]; v = bv[a]; bin = (int)((k - t_lo) >> bsh); }
       const bool kp = bin > tstar, isbd = bin == tstar;
       const unsigned mk = __ballot_sync(0xffffffffu, kp), mbd = __ballot_sync(0xffffffffu, isbd);
       int pk = 0, pb = 0;
@@ -514,7 +546,7 @@ __global__ void __launch_bounds__(1024) boundary_kernel(const PilotParams Q, con
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (only_flagged && Q.flags[b] == 0) return;
   if (n_valid[b] == 0) return;
-  const int R = Q.R, nseg = Q.nseg;
+  const int R = Q.R, nseg = Q.nsub;          // the band is walked sub-segment by sub-segment
   const int ns = Q.tot[b * 4 + 0], nb = Q.tot[b * 4 + 1], nout = Q.tot[b * 4 + 2], nbd = Q.tot[b * 4 + 3];
   const uint64_t t_hi = Q.t_hi[b], t_lo = Q.t_lo[b];
   __syncthreads();     // everybody has read the image's state before it may be reset
@@ -548,11 +580,11 @@ __global__ void __launch_bounds__(1024) boundary_kernel(const PilotParams Q, con
   }
   const uint64_t* __restrict__ bdk = Q.bd_k + (size_t)b * BD_CAP;
   const uint32_t* __restrict__ bdv = Q.bd_v + (size_t)b * BD_CAP;
-  const size_t seg0 = (size_t)b * nseg * (size_t)Q.seg_cap;
+  const size_t seg0 = (size_t)b * nseg * (size_t)Q.sub_cap;
   const uint64_t* __restrict__ bk = Q.band_k + seg0;
   const uint32_t* __restrict__ bv = Q.band_v + seg0;
   const int* __restrict__ cb = Q.cnt_band + (size_t)b * nseg;
-  const size_t cap = (size_t)Q.seg_cap;
+  const size_t cap = (size_t)Q.sub_cap;
   // visit every entry of the boundary bin as (k_, v_): the small list, or -- overflow -- the band filtered by bin
 #define PLD_FOR_BD(BODY)                                                   \
   if (!overflow) {                                                         \
@@ -562,12 +594,22 @@ __global__ void __launch_bounds__(1024) boundary_kernel(const PilotParams Q, con
       BODY                                                                 \
     }                                                                      \
   } else {                                                                 \
-    for (int c_ = wid; c_ < nseg; c_ += 32) {                              \
-      const int cnt_ = cb[c_];                                             \
-      for (int i_ = lane; i_ < cnt_; i_ += 32) {                           \
-        const uint64_t k_ = bk[(size_t)c_ * cap + (size_t)i_];             \
+    /* a warp walks the eight sub-segments of one scoring CTA as one virtual array (full lanes) */ \
+    for (int g_ = wid; g_ < nseg / 8; g_ += 32) {                          \
+      int ps_[9];                                                          \
+      ps_[0] = 0;                                                          \
+      _Pragma("unroll") for (int u_ = 0; u_ < 8; ++u_) ps_[u_ + 1] = ps_[u_] + cb[g_ * 8 + u_]; \
+      for (int i_ = lane; i_ < ps_[8]; i_ += 32) {                         \
+        int base_ = 0, off_ = i_;                                          \
+        _Pragma("unroll") for (int u_ = 1; u_ < 8; ++u_) {                 \
+          const bool ge_ = i_ >= ps_[u_];                                  \
+          base_ = ge_ ? u_ * (int)cap : base_;                             \
+          off_ = ge_ ? i_ - ps_[u_] : off_;                                \
+        }                                                                  \
+        const size_t a_ = (size_t)g_ * 8 * cap + (size_t)(base_ + off_);   \
+        const uint64_t k_ = bk[a_];                                        \
         if ((int)((k_ - t_lo) >> bsh) != tstar) continue;                  \
-        const uint32_t v_ = bv[(size_t)c_ * cap + (size_t)i_];             \
+        const uint32_t v_ = bv[a_];                                        \
         BODY                                                               \
       }                                                                    \
     }                                                                      \
@@ -705,8 +747,8 @@ size_t pilot_select_bytes(int B, int n, int R, int num_sms, size_t* offs) {
   offs[3] = take(sizeof(int) * B);                 // flags
   offs[4] = take(sizeof(int) * 4 * (size_t)B);     // tot
   offs[5] = take(sizeof(unsigned int) * (size_t)B * RS_BINS);   // hist
-  offs[6] = take(sizeof(int) * (size_t)B * nseg);  // cnt_sure
-  offs[7] = take(sizeof(int) * (size_t)B * nseg);  // cnt_band
+  offs[6] = take(sizeof(int) * (size_t)B * nseg * 8);  // cnt_sure (per warp sub-segment)
+  offs[7] = take(sizeof(int) * (size_t)B * nseg * 8);  // cnt_band
   offs[8] = take(sizeof(uint32_t) * ent);          // sure ids
   offs[9] = take(sizeof(uint64_t) * ent);          // band keys
   offs[10] = take(sizeof(uint32_t) * ent);         // band ids
@@ -756,6 +798,8 @@ static void pilot_params(int B, int n, int R, int low_bits_zero, void* scratch, 
   Q.bd_k = (uint64_t*)(sb + offs[11]); Q.bd_v = (uint32_t*)(sb + offs[12]);
   Q.order = (uint32_t*)(sb + offs[13]); Q.order_out = order_out;
   pilot_geometry(B, n, num_sms, &Q.nseg, &Q.seg_cap);
+  Q.nsub = Q.nseg * 8;
+  Q.sub_cap = Q.seg_cap / 8;
   Q.R = R;
   Q.S = n < PILOT_SAMPLE ? n : PILOT_SAMPLE;
   int pad = 256;

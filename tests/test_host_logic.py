@@ -85,3 +85,34 @@ def test_algorithmic_bytes_match_the_survey_figures():
         L = B * R
         got = bench.algorithmic_bytes(B, H * W, L, K) / L
         assert abs(got - want) < 0.3, (got, want)     # the survey rounds to three digits
+
+
+def test_comparator_networks_sort_and_match_the_committed_header():
+    """pld_oem_networks.cuh (ordering networks of the thread-per-list scoring pass) is generated: the generator's
+    networks sort (random and 0-1 inputs, descending) and the committed header is exactly what it writes."""
+    import importlib.util
+    import os
+    import random
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_oem_network", os.path.join(root, "tools", "gen_oem_network.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    rnd = random.Random(5)
+    header = open(os.path.join(root, "pldepth_b200", "csrc", "pld_oem_networks.cuh")).read()
+    for n in gen.SIZES:
+        ces = gen.network(n)
+        assert all(0 <= a < b < n for a, b in ces)
+        for hi in (1, 7, 1 << 31):
+            for _ in range(300):
+                v = [rnd.randint(0, hi) for _ in range(n)]
+                w = v[:]
+                for a, b in ces:
+                    if w[a] < w[b]:
+                        w[a], w[b] = w[b], w[a]
+                assert w == sorted(v, reverse=True)
+        assert "// N = %d: %d comparators" % (n, len(ces)) in header
+        block = header[header.index("struct OemNetwork<%d>" % n):]
+        block = block[:block.index("#undef PLD_OEM_CE")]
+        listed = [(int(a), int(b)) for a, b in re.findall(r"PLD_OEM_CE\((\d+), (\d+)\)", block)]
+        assert listed == ces, "pld_oem_networks.cuh is stale: run tools/gen_oem_network.py"

@@ -116,3 +116,30 @@ def test_comparator_networks_sort_and_match_the_committed_header():
         block = block[:block.index("#undef PLD_OEM_CE")]
         listed = [(int(a), int(b)) for a, b in re.findall(r"PLD_OEM_CE\((\d+), (\d+)\)", block)]
         assert listed == ces, "pld_oem_networks.cuh is stale: run tools/gen_oem_network.py"
+
+
+def test_numpy_pairwise_sum_is_eight_strided_accumulators():
+    """What the scoring kernels rely on (pld_score.cuh: np_pairwise_sum; pld_score_reg.cu, pld_lists_tab.cu): NumPy's
+    float32 sum of 8 <= n <= 128 contiguous terms equals eight strided accumulators r[j] = a[j] + a[8 + j] + ...
+    combined as ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), then the tail added in order; n < 8 is sequential."""
+    import numpy as np
+    rs = np.random.RandomState(11)
+    f = np.float32
+    for n in list(range(1, 40)) + [50, 56, 64, 100, 127, 128]:
+        for _ in range(20):
+            a = (rs.rand(n) * 10.0 ** rs.randint(-6, 3)).astype(np.float32)
+            if n < 8:
+                want = f(0)
+                for x in a:
+                    want = f(want + x)
+            else:
+                r = [f(a[j]) for j in range(8)]
+                n8 = n - n % 8
+                for i in range(8, n8, 8):
+                    for j in range(8):
+                        r[j] = f(r[j] + a[i + j])
+                want = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+                for i in range(n8, n):
+                    want = f(want + a[i])
+            got = np.add.reduce(a)
+            assert got.dtype == np.float32 and got.tobytes() == np.float32(want).tobytes(), (n, got, want)

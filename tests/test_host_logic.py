@@ -143,3 +143,36 @@ def test_numpy_pairwise_sum_is_eight_strided_accumulators():
                     want = f(want + a[i])
             got = np.add.reduce(a)
             assert got.dtype == np.float32 and got.tobytes() == np.float32(want).tobytes(), (n, got, want)
+
+
+def test_depth_relation_margin_test_never_disagrees_with_the_division():
+    """ScoreCfg::c_in / c_out (pld_score.cuh: relation_equal): for a >= c > 0 the scoring kernels decide
+    get_depth_relation (depth_utils.py:5-21) without dividing whenever a < c * thr_hi (1 - 2^-20) ("equal": the rounded
+    ratio is below thr_hi, and >= 1 > thr_lo) or a > c * thr_hi (1 + 2^-20) ("not equal").  Emulated here in float32:
+    wherever the margin test decides, the exact rounded division agrees -- including ratios within a few ulps of the
+    margins and of the threshold itself."""
+    import numpy as np
+    f = np.float32
+    rs = np.random.RandomState(3)
+    for threshold in (0.03, 0.25, 1e-3, 2.0):
+        thr_hi, thr_lo = 1.0 + threshold, 1.0 / (1.0 + threshold)
+        thr_hi_f, thr_lo_f = f(thr_hi), f(thr_lo)
+        c_in, c_out = f(thr_hi * (1.0 - 2.0 ** -20)), f(thr_hi * (1.0 + 2.0 ** -20))
+        assert c_in < thr_hi_f < c_out and thr_lo_f < 1.0
+        c = (rs.rand(400000) * 10.0 ** rs.randint(-6, 4, size=400000)).astype(np.float32) + f(1e-10)
+        # ratios spread over [1, 2 thr_hi], plus clusters hugging the threshold and both margins
+        ratio = np.concatenate([1.0 + rs.rand(100000) * (2 * thr_hi - 1.0),
+                                thr_hi * (1.0 + (rs.rand(100000) - 0.5) * 2.0 ** -18),
+                                thr_hi * (1.0 - 2.0 ** -20) * (1.0 + (rs.rand(100000) - 0.5) * 2.0 ** -21),
+                                thr_hi * (1.0 + 2.0 ** -20) * (1.0 + (rs.rand(100000) - 0.5) * 2.0 ** -21)])
+        a = (c.astype(np.float64) * ratio).astype(np.float32)
+        keep = a >= c
+        a, c = a[keep], c[keep]
+        inside = a < (c * c_in)                       # float32 products, as __fmul_rn
+        outside = a > (c * c_out)
+        r = a / c                                     # float32 division, round to nearest
+        equal = ~(r >= thr_hi_f) & ~(r <= thr_lo_f)
+        assert not (inside & outside).any()
+        assert equal[inside].all()
+        assert not equal[outside].any()
+        assert (inside | outside).mean() > 0.5        # the exact path is the exception
